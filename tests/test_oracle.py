@@ -1,0 +1,85 @@
+"""CPU tests: the oracle restatement is pinned against (a) the golden vectors produced by the
+unmodified reference and (b) the compiled reference itself on fresh random inputs."""
+import numpy as np
+import pytest
+
+from checkers import (Oracle, Reference, filter_counts, have_reference, sha16, to_bpp)
+from golden_cases import case_id, cases, load_input
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return Oracle()
+
+
+def check_case(oracle, c):
+    img = load_input(c, oracle)
+    if img is None:
+        pytest.skip("reference suite not present")
+    assert sha16(img) == c["in_sha"], "input generator / fixture drifted"
+    px, rf = oracle.optimize(img, c["strength"], c["bleed"], c["filters"])
+    assert sha16(px) == c["px_sha"]
+    if c["filters"]:
+        assert sha16(rf) == c["filt_sha"]
+        assert filter_counts(rf) == c["nsuap"]
+
+
+@pytest.mark.parametrize("c", cases("small"), ids=case_id)
+def test_oracle_matches_golden_small(oracle, c):
+    check_case(oracle, c)
+
+
+@pytest.mark.parametrize("c", cases("medium", "suite"), ids=case_id)
+def test_oracle_matches_golden_medium(oracle, c):
+    check_case(oracle, c)
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("c", cases("large"), ids=case_id)
+def test_oracle_matches_golden_large(oracle, c):
+    check_case(oracle, c)
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+def test_oracle_matches_reference_random(oracle):
+    """Fresh random shapes / strengths / bleeds / bpp paths, byte-for-byte against the reference."""
+    ref = Reference()
+    rng = np.random.default_rng(20260101)
+    for i in range(60):
+        w = int(rng.integers(1, 80))
+        h = int(rng.integers(1, 40))
+        bpp = int(rng.integers(1, 5))
+        kind = i % 3
+        if kind == 0:
+            img = oracle.synth(w, h, 5000 + i)
+        elif kind == 1:
+            img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)          # white noise
+        else:
+            img = (rng.integers(0, 4, (h, w, 4)) * 85).astype(np.uint8)    # few levels, many ties
+        if rng.random() < 0.5:
+            img[rng.random((h, w)) < 0.2, 3] = 0                            # transparent holes
+        img = to_bpp(img, bpp)
+        s = int(rng.choice([0, 1, 2, 7, 19, 20, 40, 85, 200, 255]))
+        b = int(rng.choice([1, 2, 3, 16, 32767]))
+        nf = bool(rng.random() < 0.7)
+        a = ref.optimize(img, s, b, nf)
+        o = oracle.optimize(img, s, b, nf)
+        assert np.array_equal(a[0], o[0]), (i, w, h, bpp, s, b, nf)
+        if nf:
+            assert np.array_equal(a[1], o[1]), (i, w, h, bpp, s, b, nf)
+
+
+def test_strength_zero_is_identity(oracle):
+    img = oracle.synth(40, 20, 9)
+    px, _ = oracle.optimize(img, 0, 2, True)
+    assert np.array_equal(px, img)
+
+
+def test_trace_cost_identity(oracle):
+    """Row cost restructuring used on the GPU: the bit cost of a row equals
+    sum_s dcount[s] * (33 + clz32(freq_end[s])).  Checked through the trace."""
+    img = oracle.synth(33, 12, 77)
+    px, rf, tr = oracle.optimize(img, 20, 2, True, trace=True)
+    assert tr["final_frequency"].sum() == 33 * 12 * 4
+    assert (tr["row_costs"].min(axis=1) < np.iinfo(np.uint64).max).all()
+    assert (tr["row_strength"] == 20).all()
