@@ -1,0 +1,133 @@
+/* pngloss_b200 - C ABI of the B200-native quantise + filter-search path of pngloss.
+ *
+ * The library (pngloss_b200/libpngloss_b200.so) is plain C at the boundary: pointers and sizes only,
+ * no CUDA or torch types.  It contains no CPU implementation of the path: every entry point runs the
+ * sm_100a kernels and fails with PNGLOSS_B200_DEVICE_ERROR when no usable device is present.
+ *
+ * Part 1 is the drop-in: the three public symbols of the reference's src/pngloss_image.h with the
+ * same names, argument meaning, in-place behaviour and error codes, so that the reference's
+ * src/pngloss.c:266 call site links against this library unchanged.
+ * Part 2 adds what the reference does not have: a batch entry (the reference loops over files one
+ * call at a time, src/pngloss.c:173-205) and a device-resident batch object for pipelines and
+ * benchmarking.
+ */
+#ifndef PNGLOSS_B200_H
+#define PNGLOSS_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Error codes: the subset of the reference's pngloss_error (src/rwpng.h:23-38) this path can
+ * return, plus one value of our own for device failures. */
+#define PNGLOSS_B200_SUCCESS 0
+#define PNGLOSS_B200_INVALID_ARGUMENT 4   /* reference INVALID_ARGUMENT */
+#define PNGLOSS_B200_OUT_OF_MEMORY 17     /* reference OUT_OF_MEMORY_ERROR (host or device) */
+#define PNGLOSS_B200_DEVICE_ERROR 40      /* no CUDA device / kernel or copy failed (new) */
+#define PNGLOSS_B200_NO_ACCEPTABLE_ROW 41 /* the reference abort()s here, src/pngloss_image.c:268 */
+
+/* ------------------------------------------------------------------------------------------------
+ * Part 1 - drop-in for reference src/pngloss_image.h.
+ * When the reference's own header is included first these prototypes are skipped; the symbols the
+ * library exports are ABI-identical (pngloss_error is a 4-byte enum, uint_fast8_t is unsigned char,
+ * int_fast16_t is long on x86-64 SysV).
+ * ---------------------------------------------------------------------------------------------- */
+#ifndef PNGLOSS_IMAGE_H
+/* replaces reference src/pngloss_image.c:52 (declared src/pngloss_image.h:21-25).
+ * rows[y] -> width*4 RGBA8 bytes, quantised in place; row_filters[height] receives libpng filter
+ * masks 0x08/0x10/0x20/0x40/0x80, or may be NULL, in which case every row is checked against
+ * libpng's own filter heuristic.  Returns 0 or 17; other failures abort() like the reference. */
+int optimize_with_rows(unsigned char **rows, uint32_t width, uint32_t height,
+                       unsigned char *row_filters, bool verbose,
+                       uint_fast8_t quantization_strength, int_fast16_t bleed_divider);
+/* replaces reference src/pngloss_image.c:40 (row_filters = NULL) */
+void optimize_with_stride(unsigned char *pixels, uint32_t width, uint32_t height, uint32_t stride,
+                          bool verbose, uint_fast8_t quantization_strength,
+                          int_fast16_t bleed_divider);
+/* replaces reference src/pngloss_image.c:29 (bleed 2, tight stride, row_filters = NULL) */
+void optimizeForAverageFilter(unsigned char pixels[], int width, int height, int quantization);
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * Part 2 - batch and device-resident entry points (new).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pngloss_b200_ctx pngloss_b200_ctx;
+typedef struct pngloss_b200_batch pngloss_b200_batch;
+
+int pngloss_b200_device_count(void);
+/* One context per GPU and host thread.  cuda_stream: a cudaStream_t to enqueue on, or NULL to let
+ * the context create its own non-blocking stream. */
+int pngloss_b200_ctx_create(pngloss_b200_ctx **out, int device, void *cuda_stream);
+void pngloss_b200_ctx_destroy(pngloss_b200_ctx *ctx);
+/* Human readable description of the last failure on this context ("" if none). */
+const char *pngloss_b200_ctx_error(const pngloss_b200_ctx *ctx);
+/* Lane mapping of the quantise kernel: lanes per colour channel = 8, 4, 2 or 1, i.e. 1, 2, 4 or 8
+ * images per CTA; 0 = choose from the batch size.  A tuning knob, results never depend on it. */
+int pngloss_b200_ctx_set_lanes(pngloss_b200_ctx *ctx, int lanes_per_channel);
+/* CUDA-event stopwatch on the context's stream (what bench.py times with). */
+int pngloss_b200_ctx_timer_start(pngloss_b200_ctx *ctx);
+int pngloss_b200_ctx_timer_stop(pngloss_b200_ctx *ctx, float *milliseconds);
+int pngloss_b200_ctx_sync(pngloss_b200_ctx *ctx);
+/* Pinned host memory for fast uploads / downloads. */
+void *pngloss_b200_host_alloc(size_t bytes);
+void pngloss_b200_host_free(void *p);
+
+typedef struct {
+    unsigned char *pixels;      /* RGBA8, quantised in place */
+    size_t stride;              /* bytes between rows, >= width * 4 */
+    uint32_t width, height;
+    unsigned char *row_filters; /* height bytes, or NULL = all rows adaptive (see above) */
+    uint32_t force_bytes_per_pixel; /* 0 = detect gray / opaque like optimize_with_rows;
+                                       1..4 = explicit mode like the reference's optimize_image
+                                       (src/pngloss_image.c:159) on RGBA-laid-out input */
+    uint32_t bytes_per_pixel;   /* out: colour mode used */
+    uint32_t retried_rows;      /* out: strength decrements that were needed (normally 0) */
+    int status;                 /* out: PNGLOSS_B200_* for this image */
+} pngloss_b200_image;
+
+/* Upload, run, download a batch of independent images.  Blocking.  Returns the first non-zero
+ * per-image status, or 0. */
+int pngloss_b200_optimize_batch(pngloss_b200_ctx *ctx, pngloss_b200_image *images, size_t n,
+                                unsigned strength, long bleed);
+
+/* Device-resident batch: allocate once, then upload / run / download as often as wanted. */
+int pngloss_b200_batch_create(pngloss_b200_ctx *ctx, size_t n, const uint32_t *widths,
+                              const uint32_t *heights, pngloss_b200_batch **out);
+void pngloss_b200_batch_destroy(pngloss_b200_batch *b);
+/* adaptive_all / force_bytes_per_pixel per image; defaults 0 / 0 */
+int pngloss_b200_batch_set_mode(pngloss_b200_batch *b, size_t i, int adaptive_all,
+                                uint32_t force_bytes_per_pixel);
+int pngloss_b200_batch_upload(pngloss_b200_batch *b, size_t i, const unsigned char *pixels,
+                              size_t stride);                     /* async on the ctx stream */
+int pngloss_b200_batch_upload_rows(pngloss_b200_batch *b, size_t i, unsigned char *const *rows);
+int pngloss_b200_batch_synth(pngloss_b200_batch *b, size_t i, uint64_t seed); /* SURVEY 8d generator */
+int pngloss_b200_batch_run(pngloss_b200_batch *b, unsigned strength, long bleed); /* async */
+int pngloss_b200_batch_download(pngloss_b200_batch *b, size_t i, unsigned char *pixels,
+                                size_t stride, unsigned char *row_filters);  /* async */
+int pngloss_b200_batch_download_rows(pngloss_b200_batch *b, size_t i, unsigned char *const *rows,
+                                     unsigned char *row_filters);
+int pngloss_b200_batch_download_input(pngloss_b200_batch *b, size_t i, unsigned char *pixels,
+                                      size_t stride);
+/* Waits for the stream; fills per-image status / mode / retries (each may be NULL). */
+int pngloss_b200_batch_finish(pngloss_b200_batch *b, int *status, uint32_t *bytes_per_pixel,
+                              uint32_t *retried_rows);
+/* Per-image final symbol histogram [256] and the batch sum [256] (valid after finish). */
+int pngloss_b200_batch_image_histogram(pngloss_b200_batch *b, size_t i, uint32_t *out256);
+int pngloss_b200_batch_histogram(pngloss_b200_batch *b, uint64_t *out256);
+/* Device address of the batch sum (uint64[256]) for the caller's NCCL all-reduce. */
+void *pngloss_b200_batch_histogram_device(pngloss_b200_batch *b);
+/* Durations of the last run in milliseconds: [0] histogram kernel, [1] quantise kernel,
+ * [2] batch-histogram kernel, [3] whole run.  Valid after finish. */
+int pngloss_b200_batch_timings(pngloss_b200_batch *b, float ms[4]);
+/* Launch geometry of the last run: [0] quantise CTAs, [1] images per CTA, [2] dynamic smem bytes,
+ * [3] kernels launched. */
+int pngloss_b200_batch_launch_info(pngloss_b200_batch *b, uint32_t info[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNGLOSS_B200_H */

@@ -1,0 +1,314 @@
+"""pngloss_b200 - Python access to the B200-native quantise + filter-search path of pngloss.
+
+This package is a thin ctypes binding over the C ABI in include/pngloss_b200.h (the product is
+pngloss_b200/libpngloss_b200.so: hand-written sm_100a kernels + a C host shim).  It exists for the
+tests and bench.py; C callers link the library directly.
+
+There is no CPU implementation here: importing works without a GPU (so the ABI can be inspected),
+but every compute entry point raises if the library or a CUDA device is missing.
+"""
+import ctypes
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpngloss_b200.so")
+
+SUCCESS = 0
+INVALID_ARGUMENT = 4
+OUT_OF_MEMORY = 17
+DEVICE_ERROR = 40
+NO_ACCEPTABLE_ROW = 41
+
+# every symbol include/pngloss_b200.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "optimize_with_rows", "optimize_with_stride", "optimizeForAverageFilter",
+    "pngloss_b200_device_count", "pngloss_b200_ctx_create", "pngloss_b200_ctx_destroy",
+    "pngloss_b200_ctx_error", "pngloss_b200_ctx_set_lanes", "pngloss_b200_ctx_timer_start",
+    "pngloss_b200_ctx_timer_stop", "pngloss_b200_ctx_sync", "pngloss_b200_host_alloc",
+    "pngloss_b200_host_free", "pngloss_b200_optimize_batch", "pngloss_b200_batch_create",
+    "pngloss_b200_batch_destroy", "pngloss_b200_batch_set_mode", "pngloss_b200_batch_upload",
+    "pngloss_b200_batch_upload_rows", "pngloss_b200_batch_synth", "pngloss_b200_batch_run",
+    "pngloss_b200_batch_download", "pngloss_b200_batch_download_rows",
+    "pngloss_b200_batch_download_input", "pngloss_b200_batch_finish",
+    "pngloss_b200_batch_image_histogram", "pngloss_b200_batch_histogram",
+    "pngloss_b200_batch_histogram_device", "pngloss_b200_batch_timings",
+    "pngloss_b200_batch_launch_info",
+]
+
+
+class PnglossError(RuntimeError):
+    def __init__(self, code, msg=""):
+        super().__init__(f"pngloss_b200 error {code}: {msg}")
+        self.code = code
+
+
+class ImageDesc(ctypes.Structure):
+    """struct pngloss_b200_image (include/pngloss_b200.h)."""
+    _fields_ = [("pixels", ctypes.c_void_p), ("stride", ctypes.c_size_t),
+                ("width", ctypes.c_uint32), ("height", ctypes.c_uint32),
+                ("row_filters", ctypes.c_void_p), ("force_bytes_per_pixel", ctypes.c_uint32),
+                ("bytes_per_pixel", ctypes.c_uint32), ("retried_rows", ctypes.c_uint32),
+                ("status", ctypes.c_int)]
+
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Load libpngloss_b200.so; fails loudly when it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PnglossError(DEVICE_ERROR, f"{LIB_PATH} is missing: run `make -C pngloss_b200/csrc` "
+                           "(or __graft_entry__.build()); there is no CPU fallback")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, u32, sz, i32 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_size_t, ctypes.c_int
+    L.optimize_with_rows.argtypes = [vp, u32, u32, vp, ctypes.c_bool, ctypes.c_uint8, ctypes.c_long]
+    L.optimize_with_rows.restype = i32
+    L.optimize_with_stride.argtypes = [vp, u32, u32, u32, ctypes.c_bool, ctypes.c_uint8, ctypes.c_long]
+    L.optimize_with_stride.restype = None
+    L.optimizeForAverageFilter.argtypes = [vp, i32, i32, i32]
+    L.optimizeForAverageFilter.restype = None
+    L.pngloss_b200_device_count.restype = i32
+    L.pngloss_b200_ctx_create.argtypes = [ctypes.POINTER(vp), i32, vp]
+    L.pngloss_b200_ctx_destroy.argtypes = [vp]
+    L.pngloss_b200_ctx_destroy.restype = None
+    L.pngloss_b200_ctx_error.argtypes = [vp]
+    L.pngloss_b200_ctx_error.restype = ctypes.c_char_p
+    L.pngloss_b200_ctx_set_lanes.argtypes = [vp, i32]
+    L.pngloss_b200_ctx_timer_start.argtypes = [vp]
+    L.pngloss_b200_ctx_timer_stop.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
+    L.pngloss_b200_ctx_sync.argtypes = [vp]
+    L.pngloss_b200_host_alloc.argtypes = [sz]
+    L.pngloss_b200_host_alloc.restype = vp
+    L.pngloss_b200_host_free.argtypes = [vp]
+    L.pngloss_b200_host_free.restype = None
+    L.pngloss_b200_optimize_batch.argtypes = [vp, ctypes.POINTER(ImageDesc), sz, ctypes.c_uint,
+                                              ctypes.c_long]
+    L.pngloss_b200_batch_create.argtypes = [vp, sz, vp, vp, ctypes.POINTER(vp)]
+    L.pngloss_b200_batch_destroy.argtypes = [vp]
+    L.pngloss_b200_batch_destroy.restype = None
+    L.pngloss_b200_batch_set_mode.argtypes = [vp, sz, i32, u32]
+    L.pngloss_b200_batch_upload.argtypes = [vp, sz, vp, sz]
+    L.pngloss_b200_batch_upload_rows.argtypes = [vp, sz, vp]
+    L.pngloss_b200_batch_synth.argtypes = [vp, sz, ctypes.c_uint64]
+    L.pngloss_b200_batch_run.argtypes = [vp, ctypes.c_uint, ctypes.c_long]
+    L.pngloss_b200_batch_download.argtypes = [vp, sz, vp, sz, vp]
+    L.pngloss_b200_batch_download_rows.argtypes = [vp, sz, vp, vp]
+    L.pngloss_b200_batch_download_input.argtypes = [vp, sz, vp, sz]
+    L.pngloss_b200_batch_finish.argtypes = [vp, vp, vp, vp]
+    L.pngloss_b200_batch_image_histogram.argtypes = [vp, sz, vp]
+    L.pngloss_b200_batch_histogram.argtypes = [vp, vp]
+    L.pngloss_b200_batch_histogram_device.argtypes = [vp]
+    L.pngloss_b200_batch_histogram_device.restype = vp
+    L.pngloss_b200_batch_timings.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
+    L.pngloss_b200_batch_launch_info.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32)]
+    _lib = L
+    return L
+
+
+def device_count() -> int:
+    return load_library().pngloss_b200_device_count()
+
+
+# ---------------------------------------------------------------------------------------------------
+# Mirror of the reference interface (src/pngloss_image.h): same names, argument meaning, in-place.
+# ---------------------------------------------------------------------------------------------------
+def _row_pointers(a: np.ndarray):
+    h = a.shape[0]
+    return (ctypes.c_void_p * h)(*[a.ctypes.data + y * a.strides[0] for y in range(h)])
+
+
+def optimize_with_rows(rgba: np.ndarray, row_filters: Optional[np.ndarray], verbose: bool,
+                       quantization_strength: int, bleed_divider: int) -> int:
+    """reference src/pngloss_image.c:52 - `rgba` (h, w, 4) uint8 is quantised in place, row_filters
+    (h,) uint8 receives the libpng masks (or None)."""
+    assert rgba.dtype == np.uint8 and rgba.ndim == 3 and rgba.shape[2] == 4 and rgba.strides[1] == 4
+    h, w, _ = rgba.shape
+    rf = row_filters.ctypes.data if row_filters is not None else None
+    return load_library().optimize_with_rows(_row_pointers(rgba), w, h, rf, verbose,
+                                             quantization_strength, bleed_divider)
+
+
+def optimize_with_stride(rgba: np.ndarray, verbose: bool, quantization_strength: int,
+                         bleed_divider: int) -> None:
+    """reference src/pngloss_image.c:40"""
+    h, w, _ = rgba.shape
+    load_library().optimize_with_stride(rgba.ctypes.data, w, h, rgba.strides[0], verbose,
+                                        quantization_strength, bleed_divider)
+
+
+def optimizeForAverageFilter(rgba: np.ndarray, quantization_strength: int) -> None:
+    """reference src/pngloss_image.c:29 (tight stride, bleed 2)"""
+    assert rgba.flags["C_CONTIGUOUS"]
+    h, w, _ = rgba.shape
+    load_library().optimizeForAverageFilter(rgba.ctypes.data, w, h, quantization_strength)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Batch objects
+# ---------------------------------------------------------------------------------------------------
+class Context:
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self.lib = load_library()
+        self.handle = ctypes.c_void_p()
+        rc = self.lib.pngloss_b200_ctx_create(ctypes.byref(self.handle), device, stream)
+        if rc:
+            raise PnglossError(rc, f"cannot create a context on CUDA device {device} "
+                               "(no CPU fallback exists)")
+        self.device = device
+
+    def _check(self, rc):
+        if rc:
+            raise PnglossError(rc, self.lib.pngloss_b200_ctx_error(self.handle).decode())
+
+    def set_lanes(self, lanes_per_channel: int):
+        self._check(self.lib.pngloss_b200_ctx_set_lanes(self.handle, lanes_per_channel))
+
+    def timer_start(self):
+        self._check(self.lib.pngloss_b200_ctx_timer_start(self.handle))
+
+    def timer_stop(self) -> float:
+        ms = ctypes.c_float()
+        self._check(self.lib.pngloss_b200_ctx_timer_stop(self.handle, ctypes.byref(ms)))
+        return ms.value
+
+    def sync(self):
+        self._check(self.lib.pngloss_b200_ctx_sync(self.handle))
+
+    def pinned_empty(self, shape, dtype=np.uint8) -> np.ndarray:
+        """numpy array backed by cudaMallocHost memory (kept alive by the array's base)."""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = self.lib.pngloss_b200_host_alloc(nbytes)
+        if not p:
+            raise PnglossError(OUT_OF_MEMORY, f"cudaMallocHost({nbytes})")
+        buf = (ctypes.c_uint8 * nbytes).from_address(p)
+        arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+        _PINNED[arr.ctypes.data] = (p, self.lib)
+        return arr
+
+    def free_pinned(self, arr: np.ndarray):
+        p, lib = _PINNED.pop(arr.ctypes.data)
+        lib.pngloss_b200_host_free(p)
+
+    def optimize_batch(self, images: Sequence[np.ndarray],
+                       row_filters: Optional[Sequence[Optional[np.ndarray]]], strength: int,
+                       bleed: int, force_bpp: int = 0) -> List[dict]:
+        """Host-buffer batch: images are quantised in place.  row_filters: list of (h,) uint8 arrays,
+        entries (or the list) may be None for the reference's row_filters == NULL semantics."""
+        n = len(images)
+        descs = (ImageDesc * n)()
+        for i, a in enumerate(images):
+            assert a.dtype == np.uint8 and a.ndim == 3 and a.shape[2] == 4 and a.strides[1] == 4
+            rf = row_filters[i] if row_filters is not None else None
+            descs[i].pixels = a.ctypes.data
+            descs[i].stride = a.strides[0]
+            descs[i].width = a.shape[1]
+            descs[i].height = a.shape[0]
+            descs[i].row_filters = rf.ctypes.data if rf is not None else None
+            descs[i].force_bytes_per_pixel = force_bpp
+        rc = self.lib.pngloss_b200_optimize_batch(self.handle, descs, n, strength, bleed)
+        self._check(rc)
+        return [dict(status=d.status, bytes_per_pixel=d.bytes_per_pixel, retried_rows=d.retried_rows)
+                for d in descs]
+
+    def close(self):
+        if self.handle:
+            self.lib.pngloss_b200_ctx_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_PINNED = {}
+
+
+class Batch:
+    """Device-resident batch (pngloss_b200_batch_*)."""
+
+    def __init__(self, ctx: Context, widths: Sequence[int], heights: Sequence[int]):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.n = len(widths)
+        self.widths = np.asarray(widths, np.uint32)
+        self.heights = np.asarray(heights, np.uint32)
+        self.handle = ctypes.c_void_p()
+        ctx._check(self.lib.pngloss_b200_batch_create(ctx.handle, self.n, self.widths.ctypes.data,
+                                                      self.heights.ctypes.data,
+                                                      ctypes.byref(self.handle)))
+
+    def set_mode(self, i, adaptive_all=False, force_bpp=0):
+        self.ctx._check(self.lib.pngloss_b200_batch_set_mode(self.handle, i, int(adaptive_all), force_bpp))
+
+    def upload(self, i, rgba: np.ndarray):
+        assert rgba.shape == (self.heights[i], self.widths[i], 4) and rgba.strides[1] == 4
+        self.ctx._check(self.lib.pngloss_b200_batch_upload(self.handle, i, rgba.ctypes.data,
+                                                           rgba.strides[0]))
+
+    def synth(self, i, seed):
+        self.ctx._check(self.lib.pngloss_b200_batch_synth(self.handle, i, seed))
+
+    def run(self, strength, bleed):
+        self.ctx._check(self.lib.pngloss_b200_batch_run(self.handle, strength, bleed))
+
+    def download(self, i, rgba: Optional[np.ndarray] = None, row_filters: Optional[np.ndarray] = None):
+        self.ctx._check(self.lib.pngloss_b200_batch_download(
+            self.handle, i, rgba.ctypes.data if rgba is not None else None,
+            rgba.strides[0] if rgba is not None else 0,
+            row_filters.ctypes.data if row_filters is not None else None))
+
+    def download_input(self, i, rgba: np.ndarray):
+        self.ctx._check(self.lib.pngloss_b200_batch_download_input(self.handle, i, rgba.ctypes.data,
+                                                                   rgba.strides[0]))
+
+    def finish(self):
+        st = np.zeros(self.n, np.int32)
+        bpp = np.zeros(self.n, np.uint32)
+        rt = np.zeros(self.n, np.uint32)
+        rc = self.lib.pngloss_b200_batch_finish(self.handle, st.ctypes.data, bpp.ctypes.data,
+                                                rt.ctypes.data)
+        if rc and rc != NO_ACCEPTABLE_ROW:
+            self.ctx._check(rc)
+        return st, bpp, rt
+
+    def image_histogram(self, i) -> np.ndarray:
+        out = np.zeros(256, np.uint32)
+        self.ctx._check(self.lib.pngloss_b200_batch_image_histogram(self.handle, i, out.ctypes.data))
+        return out
+
+    def histogram(self) -> np.ndarray:
+        out = np.zeros(256, np.uint64)
+        self.ctx._check(self.lib.pngloss_b200_batch_histogram(self.handle, out.ctypes.data))
+        return out
+
+    def histogram_device_ptr(self) -> int:
+        return self.lib.pngloss_b200_batch_histogram_device(self.handle)
+
+    def timings(self):
+        ms = (ctypes.c_float * 4)()
+        self.ctx._check(self.lib.pngloss_b200_batch_timings(self.handle, ms))
+        return dict(k1_hist_ms=ms[0], k2_quantize_ms=ms[1], k3_batch_hist_ms=ms[2], run_ms=ms[3])
+
+    def launch_info(self):
+        info = (ctypes.c_uint32 * 4)()
+        self.ctx._check(self.lib.pngloss_b200_batch_launch_info(self.handle, info))
+        return dict(k2_ctas=info[0], images_per_cta=info[1], k2_smem_bytes=info[2], launches=info[3])
+
+    def close(self):
+        if self.handle:
+            self.lib.pngloss_b200_batch_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

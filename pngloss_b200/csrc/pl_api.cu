@@ -1,0 +1,639 @@
+// Host shim: the C ABI of include/pngloss_b200.h on top of the kernels in pl_kernels.cuh.
+//
+// There is deliberately no CPU implementation of the path in this file or anywhere in the library:
+// when CUDA is unavailable every entry point fails (PNGLOSS_B200_DEVICE_ERROR).
+#include "../../include/pngloss_b200.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "pl_kernels.cuh"
+
+struct pngloss_b200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    int lpc = 0;
+    char err[512] = {0};
+    pngloss_b200_batch *cached = nullptr;   // last batch built by pngloss_b200_optimize_batch
+};
+
+struct pngloss_b200_batch {
+    pngloss_b200_ctx *ctx = nullptr;
+    size_t n = 0;
+    std::vector<uint32_t> w, h;
+    std::vector<PlImageDev> himgs;
+    std::vector<int> order;              // image indices sorted by (w, h): equal sizes share a CTA
+    unsigned char *slab = nullptr;
+    size_t slab_bytes = 0;
+    // views into the slab
+    PlImageDev *dimgs = nullptr;
+    int *dslots = nullptr;
+    unsigned char *zero_begin = nullptr;  // region cleared before every run
+    size_t zero_bytes = 0;
+    uint32_t *chan_hist = nullptr, *flags = nullptr, *status = nullptr, *final_hist = nullptr;
+    unsigned long long *batch_hist = nullptr;
+    std::vector<int> hslots;
+    std::vector<uint32_t> hstatus;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool ran = false;
+    uint32_t info[4] = {0, 0, 0, 0};
+    bool desc_dirty = true;
+};
+
+static int set_err(pngloss_b200_ctx *ctx, int code, const char *fmt, ...) {
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof ctx->err, fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define PL_CUDA(ctx, call)                                                                     \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return set_err((ctx), e_ == cudaErrorMemoryAllocation ? PNGLOSS_B200_OUT_OF_MEMORY \
+                                                                  : PNGLOSS_B200_DEVICE_ERROR, \
+                           "%s failed: %s", #call, cudaGetErrorString(e_));                    \
+    } while (0)
+
+extern "C" int pngloss_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" int pngloss_b200_ctx_create(pngloss_b200_ctx **out, int device, void *cuda_stream) {
+    if (!out) return PNGLOSS_B200_INVALID_ARGUMENT;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev)
+        return PNGLOSS_B200_DEVICE_ERROR;
+    pngloss_b200_ctx *ctx = new (std::nothrow) pngloss_b200_ctx();
+    if (!ctx) return PNGLOSS_B200_OUT_OF_MEMORY;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return PNGLOSS_B200_DEVICE_ERROR; }
+    if (cuda_stream) {
+        ctx->stream = (cudaStream_t)cuda_stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            return PNGLOSS_B200_DEVICE_ERROR;
+        }
+        ctx->own_stream = true;
+    }
+    if (cudaEventCreate(&ctx->t0) != cudaSuccess || cudaEventCreate(&ctx->t1) != cudaSuccess) {
+        delete ctx;
+        return PNGLOSS_B200_DEVICE_ERROR;
+    }
+    *out = ctx;
+    return PNGLOSS_B200_SUCCESS;
+}
+
+extern "C" void pngloss_b200_ctx_destroy(pngloss_b200_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->cached) pngloss_b200_batch_destroy(ctx->cached);
+    if (ctx->t0) cudaEventDestroy(ctx->t0);
+    if (ctx->t1) cudaEventDestroy(ctx->t1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char *pngloss_b200_ctx_error(const pngloss_b200_ctx *ctx) { return ctx ? ctx->err : ""; }
+
+extern "C" int pngloss_b200_ctx_set_lanes(pngloss_b200_ctx *ctx, int lpc) {
+    if (!ctx || !(lpc == 0 || lpc == 1 || lpc == 2 || lpc == 4 || lpc == 8))
+        return PNGLOSS_B200_INVALID_ARGUMENT;
+    ctx->lpc = lpc;
+    return PNGLOSS_B200_SUCCESS;
+}
+
+extern "C" int pngloss_b200_ctx_timer_start(pngloss_b200_ctx *ctx) {
+    if (!ctx) return PNGLOSS_B200_INVALID_ARGUMENT;
+    PL_CUDA(ctx, cudaSetDevice(ctx->device));
+    PL_CUDA(ctx, cudaEventRecord(ctx->t0, ctx->stream));
+    return PNGLOSS_B200_SUCCESS;
+}
+
+extern "C" int pngloss_b200_ctx_timer_stop(pngloss_b200_ctx *ctx, float *ms) {
+    if (!ctx || !ms) return PNGLOSS_B200_INVALID_ARGUMENT;
+    PL_CUDA(ctx, cudaSetDevice(ctx->device));
+    PL_CUDA(ctx, cudaEventRecord(ctx->t1, ctx->stream));
+    PL_CUDA(ctx, cudaEventSynchronize(ctx->t1));
+    PL_CUDA(ctx, cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
+    return PNGLOSS_B200_SUCCESS;
+}
+
+extern "C" int pngloss_b200_ctx_sync(pngloss_b200_ctx *ctx) {
+    if (!ctx) return PNGLOSS_B200_INVALID_ARGUMENT;
+    PL_CUDA(ctx, cudaSetDevice(ctx->device));
+    PL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PNGLOSS_B200_SUCCESS;
+}
+
+extern "C" void *pngloss_b200_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void pngloss_b200_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ---- batch ---------------------------------------------------------------------------------------
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int pngloss_b200_batch_create(pngloss_b200_ctx *ctx, size_t n, const uint32_t *widths,
+                                         const uint32_t *heights, pngloss_b200_batch **out) {
+    if (!ctx || !out || !n || !widths || !heights) return PNGLOSS_B200_INVALID_ARGUMENT;
+    *out = nullptr;
+    for (size_t i = 0; i < n; i++) {
+        // the reference reader caps rowbytes * height at INT_MAX (src/rwpng.c:286-290)
+        if (!widths[i] || !heights[i] || (uint64_t)widths[i] * heights[i] * 4 > 0x7fffffffull)
+            return set_err(ctx, PNGLOSS_B200_INVALID_ARGUMENT, "image %zu: bad size %ux%u", i,
+                           widths[i], heights[i]);
+    }
+    PL_CUDA(ctx, cudaSetDevice(ctx->device));
+    pngloss_b200_batch *b = new (std::nothrow) pngloss_b200_batch();
+    if (!b) return PNGLOSS_B200_OUT_OF_MEMORY;
+    b->ctx = ctx;
+    b->n = n;
+    b->w.assign(widths, widths + n);
+    b->h.assign(heights, heights + n);
+    b->himgs.resize(n);
+    b->hstatus.resize(n * 4);
+    b->order.resize(n);
+    for (size_t i = 0; i < n; i++) b->order[i] = (int)i;
+    std::stable_sort(b->order.begin(), b->order.end(), [&](int a, int c) {
+        return b->w[a] != b->w[c] ? b->w[a] < b->w[c] : b->h[a] < b->h[c];
+    });
+
+    // slab layout
+    size_t off = 0;
+    auto take = [&](size_t bytes, size_t al) { off = align_up(off, al); size_t o = off; off += bytes; return o; };
+    const size_t o_imgs = take(n * sizeof(PlImageDev), 256);
+    const size_t o_slots = take(n * 8 * sizeof(int), 256);   // worst case: one image per CTA of 8 slots
+    const size_t o_zero = take(0, 256);
+    const size_t o_chan = take(n * PL_FILTERS * 4 * 256 * sizeof(uint32_t), 256);
+    const size_t o_flags = take(n * 2 * sizeof(uint32_t), 16);
+    const size_t o_status = take(n * 4 * sizeof(uint32_t), 16);
+    const size_t o_bhist = take(256 * sizeof(unsigned long long), 16);
+    const size_t o_zero_end = take(0, 256);
+    const size_t o_final = take(n * 256 * sizeof(uint32_t), 256);
+    std::vector<size_t> o_in(n), o_out(n), o_filt(n), o_err(n), o_cand(n);
+    for (size_t i = 0; i < n; i++) {
+        const size_t px = (size_t)widths[i] * heights[i];
+        o_in[i] = take(px * 4, 256);
+        o_out[i] = take(px * 4, 256);
+        o_filt[i] = take(heights[i], 16);
+        o_err[i] = take((size_t)2 * PL_FILTERS * 2 * (widths[i] + PL_ERR_PAD) * sizeof(short4), 256);
+        o_cand[i] = take((size_t)PL_FILTERS * widths[i] * 4, 256);
+    }
+    b->slab_bytes = align_up(off, 256);
+    cudaError_t e = cudaMalloc((void **)&b->slab, b->slab_bytes);
+    if (e != cudaSuccess) {
+        const size_t want = b->slab_bytes;
+        delete b;
+        cudaGetLastError();
+        return set_err(ctx, PNGLOSS_B200_OUT_OF_MEMORY, "cudaMalloc(%zu bytes) failed: %s", want,
+                       cudaGetErrorString(e));
+    }
+    b->dimgs = (PlImageDev *)(b->slab + o_imgs);
+    b->dslots = (int *)(b->slab + o_slots);
+    b->zero_begin = b->slab + o_zero;
+    b->zero_bytes = o_zero_end - o_zero;
+    b->chan_hist = (uint32_t *)(b->slab + o_chan);
+    b->flags = (uint32_t *)(b->slab + o_flags);
+    b->status = (uint32_t *)(b->slab + o_status);
+    b->batch_hist = (unsigned long long *)(b->slab + o_bhist);
+    b->final_hist = (uint32_t *)(b->slab + o_final);
+    for (size_t i = 0; i < n; i++) {
+        PlImageDev &d = b->himgs[i];
+        d.in = (const uchar4 *)(b->slab + o_in[i]);
+        d.out = (uchar4 *)(b->slab + o_out[i]);
+        d.filters = b->slab + o_filt[i];
+        d.chan_hist = b->chan_hist + i * PL_FILTERS * 4 * 256;
+        d.flags = b->flags + i * 2;
+        d.final_hist = b->final_hist + i * 256;
+        d.err = (short4 *)(b->slab + o_err[i]);
+        d.cand = (uchar4 *)(b->slab + o_cand[i]);
+        d.status = b->status + i * 4;
+        d.width = widths[i];
+        d.height = heights[i];
+        d.adaptive_all = 0;
+        d.force_mode = 0;
+    }
+    for (int k = 0; k < 4; k++) {
+        if (cudaEventCreate(&b->ev[k]) != cudaSuccess) {
+            pngloss_b200_batch_destroy(b);
+            return set_err(ctx, PNGLOSS_B200_DEVICE_ERROR, "cudaEventCreate failed");
+        }
+    }
+    *out = b;
+    return PNGLOSS_B200_SUCCESS;
+}
+
+extern "C" void pngloss_b200_batch_destroy(pngloss_b200_batch *b) {
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    if (b->ctx->cached == b) b->ctx->cached = nullptr;
+    for (int k = 0; k < 4; k++)
+        if (b->ev[k]) cudaEventDestroy(b->ev[k]);
+    if (b->slab) cudaFree(b->slab);
+    delete b;
+}
+
+extern "C" int pngloss_b200_batch_set_mode(pngloss_b200_batch *b, size_t i, int adaptive_all,
+                                           uint32_t force_bpp) {
+    if (!b || i >= b->n || force_bpp > 4) return PNGLOSS_B200_INVALID_ARGUMENT;
+    b->himgs[i].adaptive_all = adaptive_all ? 1u : 0u;
+    b->himgs[i].force_mode = force_bpp;
+    b->desc_dirty = true;
+    return PNGLOSS_B200_SUCCESS;
+}
+
+extern "C" int pngloss_b200_batch_upload(pngloss_b200_batch *b, size_t i, const unsigned char *pixels,
+                                         size_t stride) {
+    if (!b || i >= b->n || !pixels) return PNGLOSS_B200_INVALID_ARGUMENT;
+    pngloss_b200_ctx *ctx = b->ctx;
+    const size_t rowbytes = (size_t)b->w[i] * 4;
+    if (stride < rowbytes) return set_err(ctx, PNGLOSS_B200_INVALID_ARGUMENT, "stride < width*4");
+    PL_CUDA(ctx, cudaSetDevice(ctx->device));
+    PL_CUDA(ctx, cudaMemcpy2DAsync((void *)b->himgs[i].in, rowbytes, pixels, stride, rowbytes, b->h[i],
+                                   cudaMemcpyHostToDevice, ctx->stream));
+    return PNGLOSS_B200_SUCCESS;
+}
+
+// rows[] as the reference hands them over: usually equally spaced (src/rwpng.c lays rgba_data out
+// contiguously), but the contract allows arbitrary pointers.
+static bool constant_stride(unsigned char *const *rows, uint32_t h, size_t rowbytes, size_t *stride) {
+    if (h == 1) { *stride = rowbytes; return true; }
+    if (rows[1] < rows[0]) return false;
+    const size_t s = (size_t)(rows[1] - rows[0]);
+    if (s < rowbytes) return false;
+    for (uint32_t y = 2; y < h; y++)
+        if (rows[y] != rows[0] + (size_t)y * s) return false;
+    *stride = s;
+    return true;
+}
+
+extern "C" int pngloss_b200_batch_upload_rows(pngloss_b200_batch *b, size_t i,
+                                              unsigned char *const *rows) {
+    if (!b || i >= b->n || !rows) return PNGLOSS_B200_INVALID_ARGUMENT;
+    pngloss_b200_ctx *ctx = b->ctx;
+    const size_t rowbytes = (size_t)b->w[i] * 4;
+    size_t stride = 0;
+    if (constant_stride(rows, b->h[i], rowbytes, &stride))
+        return pngloss_b200_batch_upload(b, i, rows[0], stride);
+    PL_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (uint32_t y = 0; y < b->h[i]; y++)
+        PL_CUDA(ctx, cudaMemcpyAsync((unsigned char *)b->himgs[i].in + (size_t)y * rowbytes, rows[y],
+                                     rowbytes, cudaMemcpyHostToDevice, ctx->stream));
+    return PNGLOSS_B200_SUCCESS;
+}
+
+extern "C" int pngloss_b200_batch_synth(pngloss_b200_batch *b, size_t i, uint64_t seed) {
+    if (!b || i >= b->n) return PNGLOSS_B200_INVALID_ARGUMENT;
+    pngloss_b200_ctx *ctx = b->ctx;
+    PL_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t px = (size_t)b->w[i] * b->h[i];
+    const unsigned blocks = (unsigned)std::min<size_t>((px + 255) / 256, 148 * 16);
+    pl_k_synth<<<blocks, 256, 0, ctx->stream>>>((uchar4 *)b->himgs[i].in, b->w[i], b->h[i], seed);
+    PL_CUDA(ctx, cudaGetLastError());
+    return PNGLOSS_B200_SUCCESS;
+}
+
+template <int LPC>
+static int launch_k2(pngloss_b200_batch *b, int nblocks, unsigned strength, long bleed) {
+    pngloss_b200_ctx *ctx = b->ctx;
+    static bool attr_set[16] = {false};
+    const size_t smem = sizeof(PlCtaSmem<LPC>);
+    if (!attr_set[ctx->device & 15]) {
+        PL_CUDA(ctx, cudaFuncSetAttribute(pl_k2_quantize<LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+        attr_set[ctx->device & 15] = true;
+    }
+    pl_k2_quantize<LPC><<<nblocks, PL_K2_THREADS, smem, ctx->stream>>>(b->dimgs, b->dslots, (int)strength,
+                                                                      (int)bleed);
+    PL_CUDA(ctx, cudaGetLastError());
+    b->info[0] = (uint32_t)nblocks;
+    b->info[1] = (uint32_t)PlCfg<LPC>::CPW;
+    b->info[2] = (uint32_t)smem;
+    return PNGLOSS_B200_SUCCESS;
+}
+
+// Heuristic until measured otherwise: keep one image per CTA (lowest latency per image) while that
+// already gives every SM several CTAs; pack more images per CTA for very large batches.
+static int choose_lpc(const pngloss_b200_batch *b) {
+    if (b->ctx->lpc) return b->ctx->lpc;
+    return 8;
+}
+
+extern "C" int pngloss_b200_batch_run(pngloss_b200_batch *b, unsigned strength, long bleed) {
+    if (!b) return PNGLOSS_B200_INVALID_ARGUMENT;
+    pngloss_b200_ctx *ctx = b->ctx;
+    // same ranges as the CLI checks (reference src/pngloss.c:123,128)
+    if (strength > 255 || bleed < 1 || bleed > 32767)
+        return set_err(ctx, PNGLOSS_B200_INVALID_ARGUMENT, "strength 0..255, bleed 1..32767");
+    PL_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int lpc = choose_lpc(b);
+    const int cpw = 8 / lpc;
+    // pack equally sized images into CTAs of cpw slots
+    b->hslots.clear();
+    size_t k = 0;
+    while (k < b->n) {
+        size_t e = k;
+        while (e < b->n && e - k < (size_t)cpw && b->w[b->order[e]] == b->w[b->order[k]] &&
+               b->h[b->order[e]] == b->h[b->order[k]])
+            e++;
+        for (size_t s = 0; s < (size_t)cpw; s++) b->hslots.push_back(k + s < e ? b->order[k + s] : -1);
+        k = e;
+    }
+    const int nblocks = (int)(b->hslots.size() / cpw);
+    if (b->desc_dirty) {
+        PL_CUDA(ctx, cudaMemcpyAsync(b->dimgs, b->himgs.data(), b->n * sizeof(PlImageDev),
+                                     cudaMemcpyHostToDevice, ctx->stream));
+        b->desc_dirty = false;
+    }
+    PL_CUDA(ctx, cudaMemcpyAsync(b->dslots, b->hslots.data(), b->hslots.size() * sizeof(int),
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    PL_CUDA(ctx, cudaMemsetAsync(b->zero_begin, 0, b->zero_bytes, ctx->stream));
+
+    // K1: enough row slices per image to fill the machine, capped by the image height
+    uint32_t hmin = b->h[0];
+    for (size_t i = 1; i < b->n; i++) hmin = std::min(hmin, b->h[i]);
+    size_t want = (4 * 148 + b->n - 1) / b->n;
+    unsigned slices = (unsigned)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(want, 256), hmin));
+    PL_CUDA(ctx, cudaEventRecord(b->ev[0], ctx->stream));
+    pl_k1_orig_hist<<<(unsigned)(b->n * slices), PL_K1_THREADS, 0, ctx->stream>>>(b->dimgs, slices);
+    PL_CUDA(ctx, cudaGetLastError());
+    PL_CUDA(ctx, cudaEventRecord(b->ev[1], ctx->stream));
+    int rc;
+    switch (lpc) {
+    case 8: rc = launch_k2<8>(b, nblocks, strength, bleed); break;
+    case 4: rc = launch_k2<4>(b, nblocks, strength, bleed); break;
+    case 2: rc = launch_k2<2>(b, nblocks, strength, bleed); break;
+    default: rc = launch_k2<1>(b, nblocks, strength, bleed); break;
+    }
+    if (rc) return rc;
+    PL_CUDA(ctx, cudaEventRecord(b->ev[2], ctx->stream));
+    pl_k3_batch_hist<<<(unsigned)std::min<size_t>(b->n, 64), 256, 0, ctx->stream>>>(b->dimgs, (int)b->n,
+                                                                                    b->batch_hist);
+    PL_CUDA(ctx, cudaGetLastError());
+    PL_CUDA(ctx, cudaEventRecord(b->ev[3], ctx->stream));
+    b->info[3] = 3;
+    b->ran = true;
+    return PNGLOSS_B200_SUCCESS;
+}
+
+extern "C" int pngloss_b200_batch_download(pngloss_b200_batch *b, size_t i, unsigned char *pixels,
+                                           size_t stride, unsigned char *row_filters) {
+    if (!b || i >= b->n) return PNGLOSS_B200_INVALID_ARGUMENT;
+    pngloss_b200_ctx *ctx = b->ctx;
+    const size_t rowbytes = (size_t)b->w[i] * 4;
+    PL_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (pixels) {
+        if (stride < rowbytes) return set_err(ctx, PNGLOSS_B200_INVALID_ARGUMENT, "stride < width*4");
+        PL_CUDA(ctx, cudaMemcpy2DAsync(pixels, stride, b->himgs[i].out, rowbytes, rowbytes, b->h[i],
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (row_filters)
+        PL_CUDA(ctx, cudaMemcpyAsync(row_filters, b->himgs[i].filters, b->h[i], cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+    return PNGLOSS_B200_SUCCESS;
+}
+
+extern "C" int pngloss_b200_batch_download_rows(pngloss_b200_batch *b, size_t i,
+                                                unsigned char *const *rows, unsigned char *row_filters) {
+    if (!b || i >= b->n || !rows) return PNGLOSS_B200_INVALID_ARGUMENT;
+    pngloss_b200_ctx *ctx = b->ctx;
+    const size_t rowbytes = (size_t)b->w[i] * 4;
+    size_t stride = 0;
+    if (constant_stride(rows, b->h[i], rowbytes, &stride))
+        return pngloss_b200_batch_download(b, i, rows[0], stride, row_filters);
+    PL_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (uint32_t y = 0; y < b->h[i]; y++)
+        PL_CUDA(ctx, cudaMemcpyAsync(rows[y], (const unsigned char *)b->himgs[i].out + (size_t)y * rowbytes,
+                                     rowbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (row_filters)
+        PL_CUDA(ctx, cudaMemcpyAsync(row_filters, b->himgs[i].filters, b->h[i], cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+    return PNGLOSS_B200_SUCCESS;
+}
+
+extern "C" int pngloss_b200_batch_download_input(pngloss_b200_batch *b, size_t i, unsigned char *pixels,
+                                                 size_t stride) {
+    if (!b || i >= b->n || !pixels) return PNGLOSS_B200_INVALID_ARGUMENT;
+    pngloss_b200_ctx *ctx = b->ctx;
+    const size_t rowbytes = (size_t)b->w[i] * 4;
+    if (stride < rowbytes) return set_err(ctx, PNGLOSS_B200_INVALID_ARGUMENT, "stride < width*4");
+    PL_CUDA(ctx, cudaSetDevice(ctx->device));
+    PL_CUDA(ctx, cudaMemcpy2DAsync(pixels, stride, b->himgs[i].in, rowbytes, rowbytes, b->h[i],
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+    return PNGLOSS_B200_SUCCESS;
+}
+
+extern "C" int pngloss_b200_batch_finish(pngloss_b200_batch *b, int *status, uint32_t *bpp,
+                                         uint32_t *retried) {
+    if (!b) return PNGLOSS_B200_INVALID_ARGUMENT;
+    pngloss_b200_ctx *ctx = b->ctx;
+    PL_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (b->ran)
+        PL_CUDA(ctx, cudaMemcpyAsync(b->hstatus.data(), b->status, b->n * 4 * sizeof(uint32_t),
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+    PL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int first = PNGLOSS_B200_SUCCESS;
+    for (size_t i = 0; i < b->n; i++) {
+        const int st = !b->ran ? PNGLOSS_B200_SUCCESS
+                       : b->hstatus[i * 4 + 0] == PL_ST_OK ? PNGLOSS_B200_SUCCESS
+                                                           : PNGLOSS_B200_NO_ACCEPTABLE_ROW;
+        if (status) status[i] = st;
+        if (bpp) bpp[i] = b->hstatus[i * 4 + 1];
+        if (retried) retried[i] = b->hstatus[i * 4 + 2];
+        if (st && !first) {
+            first = st;
+            set_err(ctx, st, "image %zu: no acceptable row even at strength 0", i);
+        }
+    }
+    return first;
+}
+
+extern "C" int pngloss_b200_batch_image_histogram(pngloss_b200_batch *b, size_t i, uint32_t *out256) {
+    if (!b || i >= b->n || !out256) return PNGLOSS_B200_INVALID_ARGUMENT;
+    pngloss_b200_ctx *ctx = b->ctx;
+    PL_CUDA(ctx, cudaSetDevice(ctx->device));
+    PL_CUDA(ctx, cudaMemcpyAsync(out256, b->himgs[i].final_hist, 256 * sizeof(uint32_t),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    PL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PNGLOSS_B200_SUCCESS;
+}
+
+extern "C" int pngloss_b200_batch_histogram(pngloss_b200_batch *b, uint64_t *out256) {
+    if (!b || !out256) return PNGLOSS_B200_INVALID_ARGUMENT;
+    pngloss_b200_ctx *ctx = b->ctx;
+    PL_CUDA(ctx, cudaSetDevice(ctx->device));
+    PL_CUDA(ctx, cudaMemcpyAsync(out256, b->batch_hist, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+    PL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PNGLOSS_B200_SUCCESS;
+}
+
+extern "C" void *pngloss_b200_batch_histogram_device(pngloss_b200_batch *b) {
+    return b ? (void *)b->batch_hist : nullptr;
+}
+
+extern "C" int pngloss_b200_batch_timings(pngloss_b200_batch *b, float ms[4]) {
+    if (!b || !ms || !b->ran) return PNGLOSS_B200_INVALID_ARGUMENT;
+    pngloss_b200_ctx *ctx = b->ctx;
+    PL_CUDA(ctx, cudaSetDevice(ctx->device));
+    PL_CUDA(ctx, cudaEventSynchronize(b->ev[3]));
+    PL_CUDA(ctx, cudaEventElapsedTime(&ms[0], b->ev[0], b->ev[1]));
+    PL_CUDA(ctx, cudaEventElapsedTime(&ms[1], b->ev[1], b->ev[2]));
+    PL_CUDA(ctx, cudaEventElapsedTime(&ms[2], b->ev[2], b->ev[3]));
+    PL_CUDA(ctx, cudaEventElapsedTime(&ms[3], b->ev[0], b->ev[3]));
+    return PNGLOSS_B200_SUCCESS;
+}
+
+extern "C" int pngloss_b200_batch_launch_info(pngloss_b200_batch *b, uint32_t info[4]) {
+    if (!b || !info) return PNGLOSS_B200_INVALID_ARGUMENT;
+    memcpy(info, b->info, sizeof b->info);
+    return PNGLOSS_B200_SUCCESS;
+}
+
+// ---- host-buffer batch ---------------------------------------------------------------------------------
+extern "C" int pngloss_b200_optimize_batch(pngloss_b200_ctx *ctx, pngloss_b200_image *images, size_t n,
+                                           unsigned strength, long bleed) {
+    if (!ctx || !images || !n) return PNGLOSS_B200_INVALID_ARGUMENT;
+    std::vector<uint32_t> w(n), h(n);
+    for (size_t i = 0; i < n; i++) {
+        if (!images[i].pixels) return set_err(ctx, PNGLOSS_B200_INVALID_ARGUMENT, "image %zu: NULL pixels", i);
+        w[i] = images[i].width;
+        h[i] = images[i].height;
+    }
+    // reuse the previous allocation when the shapes repeat (a CLI or service feeding equal batches)
+    pngloss_b200_batch *b = ctx->cached;
+    if (b && (b->n != n || b->w != w || b->h != h)) {
+        pngloss_b200_batch_destroy(b);
+        b = nullptr;
+    }
+    if (!b) {
+        int rc = pngloss_b200_batch_create(ctx, n, w.data(), h.data(), &b);
+        if (rc) {
+            for (size_t i = 0; i < n; i++) images[i].status = rc;
+            return rc;
+        }
+        ctx->cached = b;
+    }
+    int rc = 0;
+    for (size_t i = 0; i < n && !rc; i++) {
+        rc = pngloss_b200_batch_set_mode(b, i, images[i].row_filters == nullptr,
+                                         images[i].force_bytes_per_pixel);
+        if (!rc) rc = pngloss_b200_batch_upload(b, i, images[i].pixels, images[i].stride);
+    }
+    if (!rc) rc = pngloss_b200_batch_run(b, strength, bleed);
+    std::vector<int> st(n);
+    std::vector<uint32_t> bpp(n), retried(n);
+    if (!rc) {
+        // pixels are only written back for images that succeeded, so a failed image stays untouched
+        // like the reference's out-of-memory path (src/pngloss_image.c:98-125)
+        rc = pngloss_b200_batch_finish(b, st.data(), bpp.data(), retried.data());
+        int rc2 = 0;
+        for (size_t i = 0; i < n && !rc2; i++)
+            if (!st[i])
+                rc2 = pngloss_b200_batch_download(b, i, images[i].pixels, images[i].stride,
+                                                  images[i].row_filters);
+        if (!rc2) rc2 = pngloss_b200_ctx_sync(ctx);
+        if (rc2) rc = rc2;
+    }
+    for (size_t i = 0; i < n; i++) {
+        images[i].status = rc && !st[i] && rc != PNGLOSS_B200_NO_ACCEPTABLE_ROW ? rc : st[i];
+        images[i].bytes_per_pixel = bpp[i];
+        images[i].retried_rows = retried[i];
+    }
+    return rc;
+}
+
+// ---- drop-in entry points (reference src/pngloss_image.h) ----------------------------------------------
+static std::mutex g_default_mu;
+static pngloss_b200_ctx *g_default_ctx = nullptr;
+
+static pngloss_b200_ctx *default_ctx() {
+    if (!g_default_ctx) {
+        int dev = 0;
+        if (const char *e = getenv("PNGLOSS_B200_DEVICE")) dev = atoi(e);
+        if (pngloss_b200_ctx_create(&g_default_ctx, dev, nullptr) != PNGLOSS_B200_SUCCESS) {
+            fprintf(stderr, "pngloss_b200: no usable CUDA device %d (there is no CPU fallback)\n", dev);
+            return nullptr;
+        }
+    }
+    return g_default_ctx;
+}
+
+static int optimize_rows_impl(unsigned char *const *rows, uint32_t width, uint32_t height,
+                              unsigned char *row_filters, bool verbose, unsigned strength, long bleed) {
+    std::lock_guard<std::mutex> lock(g_default_mu);
+    pngloss_b200_ctx *ctx = default_ctx();
+    if (!ctx) return PNGLOSS_B200_DEVICE_ERROR;
+    pngloss_b200_batch *b = nullptr;
+    int rc = pngloss_b200_batch_create(ctx, 1, &width, &height, &b);
+    if (rc) return rc;
+    int st = 0;
+    rc = pngloss_b200_batch_set_mode(b, 0, row_filters == nullptr, 0);
+    if (!rc) rc = pngloss_b200_batch_upload_rows(b, 0, rows);
+    if (!rc) rc = pngloss_b200_batch_run(b, strength, bleed);
+    if (!rc) rc = pngloss_b200_batch_finish(b, &st, nullptr, nullptr);
+    if (!rc) rc = pngloss_b200_batch_download_rows(b, 0, rows, row_filters);
+    if (!rc) rc = pngloss_b200_ctx_sync(ctx);
+    if (!rc && verbose) {
+        // same two closing lines as the reference (src/pngloss_image.c:311-325), without the spinner
+        uint32_t hist[256];
+        unsigned used = 0;
+        if (!pngloss_b200_batch_image_histogram(b, 0, hist))
+            for (int i = 0; i < 256; i++) used += hist[i] != 0;
+        fputs("  compression complete\n", stderr);
+        fprintf(stderr, "  used %u unique symbols\n", used);
+    }
+    if (rc && rc != PNGLOSS_B200_OUT_OF_MEMORY)
+        fprintf(stderr, "pngloss_b200: %s\n", pngloss_b200_ctx_error(ctx));
+    pngloss_b200_batch_destroy(b);
+    return rc;
+}
+
+extern "C" int optimize_with_rows(unsigned char **rows, uint32_t width, uint32_t height,
+                                  unsigned char *row_filters, bool verbose,
+                                  uint_fast8_t quantization_strength, int_fast16_t bleed_divider) {
+    int rc = optimize_rows_impl(rows, width, height, row_filters, verbose, quantization_strength,
+                                bleed_divider);
+    if (rc == PNGLOSS_B200_NO_ACCEPTABLE_ROW) {
+        // the reference prints and abort()s (src/pngloss_image.c:268-271)
+        fprintf(stderr, "\naborting because no good row\n");
+        abort();
+    }
+    return rc;
+}
+
+extern "C" void optimize_with_stride(unsigned char *pixels, uint32_t width, uint32_t height,
+                                     uint32_t stride, bool verbose, uint_fast8_t quantization_strength,
+                                     int_fast16_t bleed_divider) {
+    std::vector<unsigned char *> rows(height);
+    for (uint32_t i = 0; i < height; i++) rows[i] = pixels + (size_t)i * stride;
+    optimize_with_rows(rows.data(), width, height, nullptr, verbose, quantization_strength, bleed_divider);
+}
+
+extern "C" void optimizeForAverageFilter(unsigned char pixels[], int width, int height, int quantization) {
+    // "propagating half the color error is good middle ground" - bleed fixed at 2 (src/pngloss_image.c:35)
+    optimize_with_stride(pixels, (uint32_t)width, (uint32_t)height, (uint32_t)width * 4u, false,
+                         (uint_fast8_t)quantization, 2);
+}

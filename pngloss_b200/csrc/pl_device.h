@@ -1,0 +1,74 @@
+// Device-side portability shim.
+//
+// The kernels in pl_kernels.cuh are written once.  nvcc compiles them for sm_100a (the product);
+// tests/simt_emu compiles the very same text with g++ (-DPL_SIMT_EMU) to run kernel *logic* on CPU
+// fibers in the GPU-less dev container.  Everything that needs inline PTX or a CUDA-only builtin
+// is wrapped here so that the kernel bodies stay identical in both builds.
+#pragma once
+
+#ifdef PL_SIMT_EMU
+#include "simt_emu.h"
+#define PL_DYN_SMEM(name) unsigned char *name = simt::dyn_smem
+#else
+#include <cuda_runtime.h>
+#include <stdint.h>
+#define PL_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
+#define PL_FULL 0xffffffffu
+
+// ---- cp.async (LDGSTS): global -> shared without a register round trip ---------------------------
+// 4- and 8-byte forms only exist as .ca; the sources are rows this CTA itself wrote (same SM, so
+// L1 is coherent for them after the CTA barrier) or read-only input.
+__device__ __forceinline__ void pl_cp_async4(void *smem_dst, const void *gmem_src) {
+#ifdef PL_SIMT_EMU
+    simt::cp_async(smem_dst, gmem_src, 4);
+#else
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem_src) : "memory");
+#endif
+}
+__device__ __forceinline__ void pl_cp_async8(void *smem_dst, const void *gmem_src) {
+#ifdef PL_SIMT_EMU
+    simt::cp_async(smem_dst, gmem_src, 8);
+#else
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem_src) : "memory");
+#endif
+}
+__device__ __forceinline__ void pl_cp_async_wait_all() {
+#ifdef PL_SIMT_EMU
+    simt::cp_async_wait_all();
+#else
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+#endif
+}
+
+// ---- exact small-integer division by a runtime constant -------------------------------------------
+// n / d for 0 <= n < 2^17, 1 <= d < 2^15, with magic = floor(2^32 / d) + 1 precomputed (d >= 2).
+// Error bound: n * (magic*d - 2^32) <= n * d < 2^32, so the high word is exactly floor(n / d).
+// d == 1 has no 32-bit magic; callers pass magic = 0 for it and we return n.
+__device__ __forceinline__ unsigned pl_udiv_magic(unsigned n, unsigned magic) {
+    return magic ? __umulhi(n, magic) : n;
+}
+__host__ __device__ __forceinline__ unsigned pl_make_magic(unsigned d) {
+    return d <= 1 ? 0u : (unsigned)(0x100000000ull / d) + 1u;
+}
+// C-style signed division truncating toward zero, |n| < 2^17.
+__device__ __forceinline__ int pl_sdiv_magic(int n, unsigned magic) {
+    unsigned a = (unsigned)(n < 0 ? -n : n);
+    int q = (int)pl_udiv_magic(a, magic);
+    return n < 0 ? -q : q;
+}
+// n / 2^k truncating toward zero (C semantics for signed operands)
+__device__ __forceinline__ int pl_sdiv_pow2(int n, int k) {
+    return (n + ((n >> 31) & ((1 << k) - 1))) >> k;
+}
+// (2 * n) / 9 truncating toward zero for |n| < 2^16
+__device__ __forceinline__ int pl_two_ninths(int n) {
+    int m = 2 * n;
+    unsigned a = (unsigned)(m < 0 ? -m : m);
+    int q = (int)__umulhi(a, 477218589u);  // floor(2^32/9)+1
+    return m < 0 ? -q : q;
+}
+__device__ __forceinline__ int pl_sext16(int v) { return (int)(short)v; }

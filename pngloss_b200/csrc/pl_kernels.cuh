@@ -1,0 +1,661 @@
+// pngloss_b200 device kernels (sm_100a).
+//
+//   K1  pl_k1_orig_hist      per-channel 5-predictor histograms of the ORIGINAL image + the gray /
+//                            opaque format scan.         replaces reference
+//                            src/optimize_state.c:66-83 (optimize_state_init histogram loop) and
+//                            src/pngloss_image.c:64-80 (format scan)
+//   K2  pl_k2_quantize<LPC>  the row loop: 5 filter candidates per row, per-byte band quantiser with
+//                            running symbol histogram, Sierra error diffusion, row cost, winner
+//                            commit.                      replaces reference
+//                            src/pngloss_image.c:159-309 (optimize_image) and
+//                            src/optimize_state.c:114-361,390-562 (run/row/diffuse/adaptive)
+//   K3  pl_k3_batch_hist     sum of the final symbol histograms of a batch (new; feeds the one
+//                            cross-GPU all-reduce)
+//       pl_k_synth           the synthetic gradient+noise generator of SURVEY 8d (bench inputs)
+//
+// All arithmetic is integer and must stay bit-exact with the reference; see DESIGN.md for the
+// mapping and for why K2 is bound by a serial dependency chain rather than by HBM.
+#pragma once
+#include "pl_device.h"
+#include "pl_types.h"
+
+// --------------------------------------------------------------------------------------------------
+// PNG predictors (reference src/optimize_state.c:575-613)
+// --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pl_paeth(int above, int diag, int left) {
+    int p = above - diag;
+    int q = left - diag;
+    int dl = p < 0 ? -p : p;
+    int da = q < 0 ? -q : q;
+    int dd = (p + q) < 0 ? -(p + q) : (p + q);
+    return (dl <= da && dl <= dd) ? left : (da <= dd) ? above : diag;
+}
+template <int F>
+__device__ __forceinline__ int pl_predict(int above, int diag, int left) {
+    if (F == 1) return left;
+    if (F == 2) return above;
+    if (F == 3) return (above + left) >> 1;
+    if (F == 4) return pl_paeth(above, diag, left);
+    return 0;
+}
+__device__ __forceinline__ int pl_byte(unsigned v, int c) { return (int)((v >> (8 * c)) & 0xffu); }
+__device__ __forceinline__ unsigned pl_u32(uchar4 p) {
+    return (unsigned)p.x | ((unsigned)p.y << 8) | ((unsigned)p.z << 16) | ((unsigned)p.w << 24);
+}
+__device__ __forceinline__ uchar4 pl_uc4(unsigned v) {
+    return make_uchar4((unsigned char)v, (unsigned char)(v >> 8), (unsigned char)(v >> 16),
+                       (unsigned char)(v >> 24));
+}
+// |signed residual| as libpng's filter heuristic sums it (reference src/optimize_state.c:510-529)
+__device__ __forceinline__ unsigned pl_absres(int here, int pred) {
+    unsigned r = (unsigned)(here - pred) & 0xffu;
+    return r < 128u ? r : 256u - r;
+}
+
+// --------------------------------------------------------------------------------------------------
+// K1: original-image histograms + format scan.  grid = images * slices CTAs, 256 threads; CTA b
+// takes rows (b % slices), (b % slices) + slices, ... of image b / slices.
+// Algorithmic traffic: 4 B/pixel read (neighbours come from L1), 20 KB written per image.
+// --------------------------------------------------------------------------------------------------
+#define PL_K1_THREADS 256
+
+__global__ void __launch_bounds__(PL_K1_THREADS) pl_k1_orig_hist(const PlImageDev *imgs,
+                                                                  unsigned slices) {
+    __shared__ uint32_t h[PL_FILTERS * 4 * 256];
+    __shared__ uint32_t sflag[2];
+    const PlImageDev im = imgs[blockIdx.x / slices];
+    const uint32_t W = im.width, H = im.height;
+    for (int i = threadIdx.x; i < PL_FILTERS * 4 * 256; i += PL_K1_THREADS) h[i] = 0;
+    if (threadIdx.x < 2) sflag[threadIdx.x] = 0;
+    __syncthreads();
+
+    unsigned notgray = 0, notopaque = 0;
+    for (uint32_t y = blockIdx.x % slices; y < H; y += slices) {
+        const uchar4 *row = im.in + (size_t)y * W;
+        const uchar4 *up = y ? row - W : row;
+        for (uint32_t x = threadIdx.x; x < W; x += PL_K1_THREADS) {
+            const unsigned o = pl_u32(row[x]);
+            const unsigned l = x ? pl_u32(row[x - 1]) : 0u;
+            const unsigned a = y ? pl_u32(up[x]) : 0u;
+            const unsigned d = (x && y) ? pl_u32(up[x - 1]) : 0u;
+            const int r = pl_byte(o, 0), g = pl_byte(o, 1), b = pl_byte(o, 2);
+            notgray |= (unsigned)(r != g || g != b);
+            notopaque |= (unsigned)(pl_byte(o, 3) < 255);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int oc = pl_byte(o, c), lc = pl_byte(l, c), ac = pl_byte(a, c), dc = pl_byte(d, c);
+                atomicAdd(&h[(0 * 4 + c) * 256 + oc], 1u);
+                atomicAdd(&h[(1 * 4 + c) * 256 + ((oc - lc) & 255)], 1u);
+                atomicAdd(&h[(2 * 4 + c) * 256 + ((oc - ac) & 255)], 1u);
+                atomicAdd(&h[(3 * 4 + c) * 256 + ((oc - ((ac + lc) >> 1)) & 255)], 1u);
+                atomicAdd(&h[(4 * 4 + c) * 256 + ((oc - pl_paeth(ac, dc, lc)) & 255)], 1u);
+            }
+        }
+    }
+    if (notgray) sflag[0] = 1;
+    if (notopaque) sflag[1] = 1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < PL_FILTERS * 4 * 256; i += PL_K1_THREADS)
+        if (h[i]) atomicAdd(&im.chan_hist[i], h[i]);
+    if (threadIdx.x < 2 && sflag[threadIdx.x]) atomicOr(&im.flags[threadIdx.x], 1u);
+}
+
+// --------------------------------------------------------------------------------------------------
+// K2: quantise + filter search.
+//
+// One CTA = 5 warps = the 5 filter candidates of CPW images (CPW = 8 / LPC).  Inside a warp a chain
+// (image, filter) owns GROUP = 4*LPC lanes: LPC lanes for each RGBA channel.  The channels of one
+// pixel are evaluated together against the histogram as it stood at the start of the pixel and then
+// repaired in channel order (see "fix-up" below), which keeps the reference's strictly sequential
+// symbol_frequency semantics while exposing 4-way parallelism.
+// --------------------------------------------------------------------------------------------------
+template <int LPC>
+struct PlCfg {
+    static const int GROUP = 4 * LPC;    // lanes per chain
+    static const int CPW = 32 / GROUP;   // chains per warp = images per CTA
+    static const int TP = GROUP;         // pixels per tile per chain (one per lane)
+};
+
+template <int LPC>
+struct PlWarpSmem {
+    // input tiles, double buffered; slot 0 of each tile is the last pixel of the previous tile
+    uint32_t orig[2][PlCfg<LPC>::CPW][PlCfg<LPC>::TP + 1];  // original row y
+    uint32_t oa[2][PlCfg<LPC>::CPW][PlCfg<LPC>::TP + 1];    // original row y-1 ("old above")
+    uint32_t na[2][PlCfg<LPC>::CPW][PlCfg<LPC>::TP + 1];    // quantised row y-1 ("new above")
+    short4 e0[2][PlCfg<LPC>::CPW][PlCfg<LPC>::TP];          // incoming error row 0, cells x+4
+    short4 e1[2][PlCfg<LPC>::CPW][PlCfg<LPC>::TP];          // incoming error row 1, cells x+4
+    // output staging of the current tile
+    uint32_t back[PlCfg<LPC>::CPW][PlCfg<LPC>::TP + 1];     // candidate pixels (slot 0 = carry)
+    short4 n0[PlCfg<LPC>::CPW][PlCfg<LPC>::TP];             // finished cells of next error row 0
+    short4 n1[PlCfg<LPC>::CPW][PlCfg<LPC>::TP];             // finished cells of next error row 1
+};
+
+template <int LPC>
+struct PlCtaSmem {
+    uint32_t hist[PlCfg<LPC>::CPW][PL_FILTERS][256];  // running symbol histogram of every chain
+    uint32_t base[PlCfg<LPC>::CPW][256];              // histogram at the start of the row
+    uint32_t of[PlCfg<LPC>::CPW][PL_FILTERS][256];    // original_frequency for the image's mode
+    unsigned long long cost[PlCfg<LPC>::CPW][PL_FILTERS];
+    PlImageDev img[PlCfg<LPC>::CPW];
+    int win[PlCfg<LPC>::CPW];
+    int retry;
+    PlWarpSmem<LPC> w[PL_K2_WARPS];
+};
+
+// colour mode of an image: forced, or detected by K1's scan (reference src/pngloss_image.c:64-93)
+__device__ __forceinline__ int pl_image_mode(const PlImageDev &im) {
+    if (im.force_mode) return (int)im.force_mode;
+    const bool notgray = im.flags[0] != 0, notopaque = im.flags[1] != 0;
+    return notgray ? (notopaque ? 4 : 3) : (notopaque ? 2 : 1);
+}
+
+// per-lane view of its chain
+struct PlChain {
+    const uchar4 *in;
+    const uchar4 *out;
+    short4 *err;
+    uchar4 *cand;
+    int chmask;       // active RGBA channels: 0x2 gray, 0xA gray+alpha, 0x7 rgb, 0xF rgba
+    bool gray;        // gray modes count the G difference three times (color_delta.c:10-25)
+    bool alpha_rule;  // fully transparent pixels stay transparent (optimize_state.c:158-164)
+    bool live;        // chain takes part in this pass
+    int q;            // quantisation strength of this pass
+    unsigned step_magic;
+};
+
+__device__ __forceinline__ int pl_chan16(const short4 &v, int c) {
+    return ((const short *)&v)[c];
+}
+
+template <int LPC, int F>
+__device__ __noinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC> &sm, const PlChain &cn, int W,
+                                                       int y, int parity, int prev_w, bool adaptive,
+                                                       unsigned bleed_magic) {
+    typedef PlCfg<LPC> C;
+    const int lane = threadIdx.x & 31;
+    const int ci = lane / C::GROUP, gl = lane % C::GROUP;
+    const int ch = gl / LPC, sub = gl % LPC;
+    PlWarpSmem<LPC> &ws = sm.w[F];
+    uint32_t *hist = sm.hist[ci][F];
+    const uint32_t *of = sm.of[ci][F];
+    const int EW = W + PL_ERR_PAD;
+    const bool live = cn.live;
+    const bool first = (y == 0);
+    const bool act = live && ((cn.chmask >> ch) & 1);
+    const int q = cn.q, step = cn.q + 1;
+
+    const short4 *Ecur0 = cn.err + ((size_t)(parity * PL_FILTERS + prev_w) * 2 + 0) * EW;
+    const short4 *Ecur1 = Ecur0 + EW;
+    short4 *En0 = cn.err + ((size_t)((parity ^ 1) * PL_FILTERS + F) * 2 + 0) * EW;
+    short4 *En1 = En0 + EW;
+    const uchar4 *rin = cn.in + (size_t)y * W;
+    const uchar4 *rin_up = cn.in + (size_t)(y ? y - 1 : 0) * W;
+    const uchar4 *rout_up = cn.out + (size_t)(y ? y - 1 : 0) * W;
+    uchar4 *rcand = cn.cand + (size_t)F * W;
+
+    // Sierra window for this lane's channel (reference src/optimize_state.c:445-467):
+    //   a0..a2 = error row 0, cells x+2 (the one consumed by pixel x), x+3, x+4
+    //   b0..b4 = error row 1, cells x .. x+4   (becomes row 0 of the next image row)
+    //   c0..c3 = error row 2, cells x .. x+3   (becomes row 1 of the next image row; starts at zero)
+    int a0 = 0, a1 = 0, a2, b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4, c0 = 0, c1 = 0, c2 = 0, c3;
+    if (!first && live) {
+        a0 = pl_chan16(Ecur0[2], ch);
+        a1 = pl_chan16(Ecur0[3], ch);
+        b0 = pl_chan16(Ecur1[0], ch);
+        b1 = pl_chan16(Ecur1[1], ch);
+        b2 = pl_chan16(Ecur1[2], ch);
+        b3 = pl_chan16(Ecur1[3], ch);
+    }
+    int left = 0, aprev = 0;
+    unsigned long long derr = 0;
+    unsigned as0 = 0, as1 = 0, as2 = 0, as3 = 0, as4 = 0;
+
+    const int ntiles = (W + C::TP - 1) / C::TP;
+    // tile loader: lane (ci, gl) fetches pixel x0 + gl of its chain
+    auto issue = [&](int t, int buf) {
+        const int x1 = t * C::TP + gl;
+        if (x1 < W && live) {
+            pl_cp_async4(&ws.orig[buf][ci][gl + 1], rin + x1);
+            if (!first) {
+                pl_cp_async4(&ws.oa[buf][ci][gl + 1], rin_up + x1);
+                pl_cp_async4(&ws.na[buf][ci][gl + 1], rout_up + x1);
+                pl_cp_async8(&ws.e0[buf][ci][gl], Ecur0 + x1 + 4);
+                pl_cp_async8(&ws.e1[buf][ci][gl], Ecur1 + x1 + 4);
+            } else {
+                ws.oa[buf][ci][gl + 1] = 0;
+                ws.na[buf][ci][gl + 1] = 0;
+                ws.e0[buf][ci][gl] = make_short4(0, 0, 0, 0);
+                ws.e1[buf][ci][gl] = make_short4(0, 0, 0, 0);
+            }
+        }
+    };
+    issue(0, 0);
+    pl_cp_async_wait_all();
+    __syncwarp();
+
+    for (int t = 0; t < ntiles; t++) {
+        const int buf = t & 1;
+        const int x0 = t * C::TP;
+        const int npx = min(C::TP, W - x0);
+        if (t + 1 < ntiles) issue(t + 1, buf ^ 1);
+
+        for (int i = 0; i < npx; i++) {
+            // ---- fetch this lane's channel of pixel x0+i -------------------------------------
+            const int o = ((const unsigned char *)&ws.orig[buf][ci][i + 1])[ch];
+            const int a = ((const unsigned char *)&ws.na[buf][ci][i + 1])[ch];
+            a2 = pl_chan16(ws.e0[buf][ci][i], ch);
+            b4 = pl_chan16(ws.e1[buf][ci][i], ch);
+            c3 = 0;
+            int pred = pl_predict<F>(a, aprev, left);
+            const bool transp = cn.alpha_rule && ch == 3 && o == 0;
+
+            // ---- band of admissible symbols (reference src/optimize_state.c:158-210) ---------
+            int here, lo, hi, ex;
+            if (transp) {
+                here = 0;
+                lo = hi = ex = -pred;
+            } else {
+                here = o + pl_sext16(a0);
+                ex = o - pred;
+                if (ex < -128) { pred -= 256; ex += 256; }
+                else if (ex > 127) { pred += 256; ex -= 256; }
+                const int want = here - pred;
+                const unsigned m = (unsigned)(want < 0 ? -want : want);
+                const int r = (int)(m - pl_udiv_magic(m, cn.step_magic) * (unsigned)step);
+                if (want < 0) { hi = -((int)m - r); lo = hi - q; }
+                else { lo = want - r; hi = lo + q; }
+                if (lo + pred < 0) lo = -pred;
+                if (hi + pred > 255) hi = 255 - pred;
+                if (hi < lo) {
+                    if (want + pred > 255) lo = hi = 255 - pred;
+                    if (want + pred < 0) lo = hi = -pred;
+                }
+            }
+            const int span = act ? hi - lo : -1;
+
+            // ---- candidate scan against the histogram at the start of the pixel ---------------
+            // key = (symbol_frequency, original_frequency, symbol == exact), earliest symbol wins
+            // ties (reference :212-244).
+            unsigned long long bkey = 0;
+            int bpos = 0x7fff;
+            for (int pos = sub; pos <= span; pos += LPC) {
+                const int s = lo + pos;
+                const unsigned idx = (unsigned)s & 255u;
+                const unsigned long long key = ((unsigned long long)hist[idx] << 32) |
+                                               (unsigned long long)((of[idx] << 1) | (unsigned)(s == ex));
+                if (key > bkey || bpos == 0x7fff) { bkey = key; bpos = pos; }
+            }
+#pragma unroll
+            for (int mk = 1; mk < LPC; mk <<= 1) {
+                const unsigned long long okey = __shfl_xor_sync(PL_FULL, bkey, mk);
+                const int opos = __shfl_xor_sync(PL_FULL, bpos, mk);
+                if (okey > bkey || (okey == bkey && opos < bpos)) { bkey = okey; bpos = opos; }
+            }
+            unsigned bf = (unsigned)(bkey >> 32), bk2 = (unsigned)bkey;
+
+            // ---- fix-up: replay the channel order ---------------------------------------------
+            // The reference increments symbol_frequency[best] before the next channel looks at it
+            // (:253).  Raising one count can only promote that one symbol, so the true winner of
+            // channel k is either its provisional winner or one of the symbols chosen by channels
+            // 0..k-1 (with their counts as updated so far).
+#pragma unroll
+            for (int t2 = 0; t2 < 3; t2++) {
+                const int src = ci * C::GROUP + t2 * LPC;
+                const int vsym = __shfl_sync(PL_FULL, lo + bpos, src);
+                const unsigned fv = __shfl_sync(PL_FULL, bf, src);
+                const unsigned kv = __shfl_sync(PL_FULL, bk2, src);
+                if (ch > t2 && act && ((cn.chmask >> t2) & 1)) {
+                    const int pos = (vsym - lo) & 255;
+                    if (pos <= span) {
+                        if (pos == bpos) {
+                            bf += 1;
+                        } else {
+                            const unsigned f2 = fv + 1;
+                            const unsigned k2 = (kv & ~1u) | (unsigned)(lo + pos == ex);
+                            if (f2 > bf || (f2 == bf && (k2 > bk2 || (k2 == bk2 && pos < bpos)))) {
+                                bf = f2;
+                                bk2 = k2;
+                                bpos = pos;
+                            }
+                        }
+                    }
+                }
+            }
+
+            // ---- commit the byte ----------------------------------------------------------------
+            const int sym = lo + bpos;
+            const int back = act ? sym + pred : 0;
+            if (act && sub == 0) {
+                atomicAdd(&hist[(unsigned)sym & 255u], 1u);
+                ((unsigned char *)&ws.back[ci][i + 1])[ch] = (unsigned char)back;
+            }
+            left = back;
+            aprev = a;
+
+            // ---- Sierra diffusion of (here - back) / bleed (reference :390-467) ------------------
+            int dd = act ? pl_sext16(here - back) : 0;
+            dd = pl_sdiv_magic(dd, bleed_magic);
+            const int twos = pl_sdiv_pow2(dd, 4);
+            dd -= 4 * twos;
+            const int threes = pl_sdiv_pow2(dd, 3);
+            dd -= 2 * threes;
+            const int fours = pl_two_ninths(dd);
+            dd -= 2 * fours;
+            const int five = pl_sdiv_pow2(dd, 1);
+            dd -= five;
+            a1 += dd;
+            a2 += threes;
+            b0 += twos;
+            b1 += fours;
+            b2 += five;
+            b3 += fours;
+            b4 += twos;
+            c1 += twos;
+            c2 += threes;
+            c3 += twos;
+            if (sub == 0) {
+                ((short *)&ws.n0[ci][i])[ch] = (short)b0;
+                ((short *)&ws.n1[ci][i])[ch] = (short)c0;
+            }
+            a0 = a1; a1 = a2;
+            b0 = b1; b1 = b2; b2 = b3; b3 = b4;
+            c0 = c1; c1 = c2; c2 = c3;
+            __syncwarp();
+        }
+
+        // ---- tile epilogue: lane (ci, gl) owns pixel x0+gl ------------------------------------------
+        if (gl < npx && live) {
+            const int x = x0 + gl;
+            const unsigned o4 = ws.orig[buf][ci][gl + 1], q4 = ws.back[ci][gl + 1];
+            const unsigned oa4 = ws.oa[buf][ci][gl + 1], na4 = ws.na[buf][ci][gl + 1];
+            unsigned ol4 = 0, ql4 = 0, oad4 = 0, nad4 = 0;
+            if (x > 0) {
+                ol4 = ws.orig[buf][ci][gl];
+                ql4 = ws.back[ci][gl];
+                oad4 = ws.oa[buf][ci][gl];
+                nad4 = ws.na[buf][ci][gl];
+            }
+            En0[x] = ws.n0[ci][gl];
+            En1[x] = ws.n1[ci][gl];
+            rcand[x] = pl_uc4(q4);
+            // derivative error of the three neighbours (reference :265-287)
+            unsigned e = 0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                if ((cn.chmask >> c) & 1) {
+                    const int oc = pl_byte(o4, c), qc = pl_byte(q4, c);
+                    const int da = (pl_byte(oa4, c) - oc) - (pl_byte(na4, c) - qc);
+                    const int dg = (pl_byte(oad4, c) - oc) - (pl_byte(nad4, c) - qc);
+                    const int dl = (pl_byte(ol4, c) - oc) - (pl_byte(ql4, c) - qc);
+                    const unsigned s2 = (unsigned)(da * da + dg * dg + dl * dl);
+                    e += (cn.gray && c == 1) ? 3u * s2 : s2;
+                    if (adaptive) {
+                        const int lq = pl_byte(ql4, c), aq = pl_byte(na4, c), dq = pl_byte(nad4, c);
+                        as0 += pl_absres(qc, 0);
+                        as1 += pl_absres(qc, lq);
+                        as2 += pl_absres(qc, aq);
+                        as3 += pl_absres(qc, (aq + lq) >> 1);
+                        as4 += pl_absres(qc, pl_paeth(aq, dq, lq));
+                    }
+                }
+            }
+            derr += e;
+        }
+        if (gl == 0 && live) {
+            ws.orig[buf ^ 1][ci][0] = ws.orig[buf][ci][npx];
+            ws.oa[buf ^ 1][ci][0] = ws.oa[buf][ci][npx];
+            ws.na[buf ^ 1][ci][0] = ws.na[buf][ci][npx];
+            ws.back[ci][0] = ws.back[ci][npx];
+        }
+        pl_cp_async_wait_all();
+        __syncwarp();
+    }
+
+    // ---- row tail: cells W .. W+3 of the two outgoing error rows -----------------------------------
+    if (act && sub == 0) {
+        ((short *)&En0[W + 0])[ch] = (short)b0;
+        ((short *)&En0[W + 1])[ch] = (short)b1;
+        ((short *)&En0[W + 2])[ch] = (short)b2;
+        ((short *)&En0[W + 3])[ch] = (short)b3;
+        ((short *)&En1[W + 0])[ch] = (short)c0;
+        ((short *)&En1[W + 1])[ch] = (short)c1;
+        ((short *)&En1[W + 2])[ch] = (short)c2;
+        ((short *)&En1[W + 3])[ch] = 0;
+    }
+
+    // ---- row cost (reference src/optimize_state.c:314-360) -------------------------------------------
+    // bits = sum over symbols of (count gained in this row) * ulog2(UINTMAX_MAX / final count);
+    // ulog2(UINTMAX_MAX / f) == 33 + clz32(f) for every f >= 1.
+    unsigned bits = 0;
+    for (int s = gl; s < 256; s += C::GROUP) {
+        const unsigned hv = hist[s];
+        bits += (hv - sm.base[ci][s]) * (33u + (unsigned)__clz((int)hv));
+    }
+#pragma unroll
+    for (int mk = 1; mk < C::GROUP; mk <<= 1) {
+        derr += __shfl_xor_sync(PL_FULL, derr, mk);
+        bits += __shfl_xor_sync(PL_FULL, bits, mk);
+    }
+    unsigned long long cost = derr / 128ull + bits;
+    if (__any_sync(PL_FULL, adaptive)) {   // chains of one warp may differ; keep the shuffles uniform
+#pragma unroll
+        for (int mk = 1; mk < C::GROUP; mk <<= 1) {
+            as0 += __shfl_xor_sync(PL_FULL, as0, mk);
+            as1 += __shfl_xor_sync(PL_FULL, as1, mk);
+            as2 += __shfl_xor_sync(PL_FULL, as2, mk);
+            as3 += __shfl_xor_sync(PL_FULL, as3, mk);
+            as4 += __shfl_xor_sync(PL_FULL, as4, mk);
+        }
+        // libpng picks the first minimum in the order none, sub, up, average, paeth (:531-559)
+        unsigned lowest = min(min(min(as0, as1), min(as2, as3)), as4);
+        int pick = lowest >= as0 ? 0 : lowest >= as1 ? 1 : lowest >= as2 ? 2 : lowest >= as3 ? 3 : 4;
+        if (adaptive && pick != F) cost = ~0ull;
+    }
+    return cost;
+}
+
+template <int LPC>
+__global__ void __launch_bounds__(PL_K2_THREADS)
+pl_k2_quantize(const PlImageDev *imgs, const int *slots, int strength, int bleed) {
+    typedef PlCfg<LPC> C;
+    PL_DYN_SMEM(smem_raw);
+    PlCtaSmem<LPC> &sm = *(PlCtaSmem<LPC> *)smem_raw;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, F = tid >> 5;
+    const int ci = lane / C::GROUP, gl = lane % C::GROUP;
+    const int *my_slots = slots + (size_t)blockIdx.x * C::CPW;
+
+    // ---- set-up ----------------------------------------------------------------------------------------
+    if (tid < C::CPW) {
+        const int idx = my_slots[tid];
+        sm.img[tid] = imgs[idx >= 0 ? idx : my_slots[0]];
+        sm.win[tid] = 0;
+    }
+    if (tid == 0) sm.retry = 0;
+    __syncthreads();
+    const int W = (int)sm.img[0].width, H = (int)sm.img[0].height;
+    const bool valid = my_slots[ci] >= 0;
+
+    PlChain cn;
+    {
+        const PlImageDev &im = sm.img[ci];
+        const int mode = pl_image_mode(im);
+        cn.in = im.in;
+        cn.out = im.out;
+        cn.err = im.err;
+        cn.cand = im.cand;
+        cn.gray = mode <= 2;
+        cn.alpha_rule = (mode & 1) == 0;
+        cn.chmask = PL_MODE_MASK(mode);
+        cn.live = valid;
+        cn.q = strength;
+        cn.step_magic = pl_make_magic((unsigned)strength + 1u);
+    }
+    for (int k = tid; k < C::CPW * PL_FILTERS * 256; k += PL_K2_THREADS) {
+        const int c2 = k / (PL_FILTERS * 256), r = k % (PL_FILTERS * 256);
+        const int f = r / 256, s = r % 256;
+        const PlImageDev &im = sm.img[c2];
+        const int mask = PL_MODE_MASK(pl_image_mode(im));
+        unsigned v = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            if ((mask >> c) & 1) v += im.chan_hist[(f * 4 + c) * 256 + s];
+        sm.of[c2][f][s] = v;
+        sm.hist[c2][f][s] = 0;
+        if (f == 0) sm.base[c2][s] = 0;
+    }
+    __syncthreads();
+
+    const unsigned bleed_magic = pl_make_magic((unsigned)bleed);
+    int prev_w = 0;
+    bool failed = false;       // this chain's image hit "no acceptable row" (reference abort())
+    unsigned retries = 0;
+
+    for (int y = 0; y < H; y++) {
+        const bool adaptive = sm.img[ci].adaptive_all || y == 0;   // reference src/pngloss_image.c:210
+        cn.q = strength;
+        cn.step_magic = pl_make_magic((unsigned)strength + 1u);
+        cn.live = valid && !failed;
+        bool pending = cn.live;
+        for (;;) {
+            unsigned long long cost;
+            switch (F) {
+            case 0: cost = pl_row_pass<LPC, 0>(sm, cn, W, y, y & 1, prev_w, adaptive, bleed_magic); break;
+            case 1: cost = pl_row_pass<LPC, 1>(sm, cn, W, y, y & 1, prev_w, adaptive, bleed_magic); break;
+            case 2: cost = pl_row_pass<LPC, 2>(sm, cn, W, y, y & 1, prev_w, adaptive, bleed_magic); break;
+            case 3: cost = pl_row_pass<LPC, 3>(sm, cn, W, y, y & 1, prev_w, adaptive, bleed_magic); break;
+            default: cost = pl_row_pass<LPC, 4>(sm, cn, W, y, y & 1, prev_w, adaptive, bleed_magic); break;
+            }
+            if (gl == 0 && cn.live) sm.cost[ci][F] = cost;
+            __syncthreads();
+
+            // ---- pick the winner of every image that ran this pass (reference :257-263) --------------
+            int w = -1;
+            if (cn.live) {
+                unsigned long long best = ~0ull;
+#pragma unroll
+                for (int f = 0; f < PL_FILTERS; f++) {
+                    const unsigned long long c = sm.cost[ci][f];
+                    if (c < best) { best = c; w = f; }
+                }
+                if (F == 0 && gl == 0) {
+                    sm.win[ci] = w;
+                    if (w < 0 && cn.q > 0) sm.retry = 1;
+                }
+            } else if (F == 0 && gl == 0) {
+                sm.win[ci] = -2;   // not part of this pass
+            }
+            __syncthreads();
+
+            // ---- commit: all 160 threads, image by image ----------------------------------------------
+            for (int c2 = 0; c2 < C::CPW; c2++) {
+                const int w2 = sm.win[c2];
+                if (w2 == -2) continue;
+                if (w2 >= 0) {
+                    const PlImageDev &im = sm.img[c2];
+                    const int mode2 = pl_image_mode(im);
+                    const bool notgray = mode2 >= 3, notopaque = (mode2 & 1) == 0;
+                    const uchar4 *src = im.cand + (size_t)w2 * W;
+                    uchar4 *dst = im.out + (size_t)y * W;
+                    for (int x = tid; x < W; x += PL_K2_THREADS) {
+                        uchar4 p = src[x];
+                        if (!notgray) { p.x = p.y; p.z = p.y; }   // widen gray (pngloss_image.c:130-139)
+                        if (!notopaque) p.w = 255;               // strip alpha (:134,:144)
+                        dst[x] = p;
+                    }
+                    for (int s = tid; s < 256; s += PL_K2_THREADS) {
+                        const unsigned v = sm.hist[c2][w2][s];
+                        sm.base[c2][s] = v;
+#pragma unroll
+                        for (int f = 0; f < PL_FILTERS; f++) sm.hist[c2][f][s] = v;
+                    }
+                    if (tid == 0) im.filters[y] = (unsigned char)(0x08 << w2);
+                } else {
+                    // nobody acceptable: restore the histograms for the retry at lower strength
+                    for (int s = tid; s < 256; s += PL_K2_THREADS) {
+                        const unsigned v = sm.base[c2][s];
+#pragma unroll
+                        for (int f = 0; f < PL_FILTERS; f++) sm.hist[c2][f][s] = v;
+                    }
+                }
+            }
+            const bool again = sm.retry != 0;
+            if (pending) {
+                if (w >= 0) {
+                    prev_w = w;
+                    pending = false;
+                } else if (cn.q == 0) {
+                    failed = true;     // reference aborts here (src/pngloss_image.c:268-271)
+                    pending = false;
+                } else {
+                    cn.q -= 1;         // try again at lower quantization strength (:273-274)
+                    cn.step_magic = pl_make_magic((unsigned)cn.q + 1u);
+                    retries++;
+                }
+            }
+            cn.live = pending;
+            __syncthreads();
+            if (tid == 0) sm.retry = 0;   // next write happens only after the next cost barrier
+            if (!again) break;
+        }
+    }
+
+    // ---- results -------------------------------------------------------------------------------------------
+    for (int c2 = 0; c2 < C::CPW; c2++) {
+        if (my_slots[c2] < 0) continue;
+        const PlImageDev &im = sm.img[c2];
+        for (int s = tid; s < 256; s += PL_K2_THREADS) im.final_hist[s] = sm.base[c2][s];
+    }
+    if (valid && F == 0 && gl == 0) {
+        const PlImageDev &im = sm.img[ci];
+        im.status[0] = failed ? PL_ST_NO_ROW : PL_ST_OK;
+        im.status[1] = cn.gray ? (cn.alpha_rule ? 2u : 1u) : (cn.alpha_rule ? 4u : 3u);
+        im.status[2] = retries;
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// K3: batch histogram.  out[256] (u64) += sum over images of final_hist.  grid = any, 256 threads.
+// --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pl_k3_batch_hist(const PlImageDev *imgs, int n,
+                                                        unsigned long long *out) {
+    unsigned long long acc = 0;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) acc += imgs[i].final_hist[threadIdx.x];
+    if (acc) atomicAdd(&out[threadIdx.x], acc);
+}
+
+// --------------------------------------------------------------------------------------------------
+// Synthetic gradient + noise RGBA image, identical to oracle_synth_rgba.
+// --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long pl_splitmix64(unsigned long long z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256) pl_k_synth(uchar4 *dst, uint32_t w, uint32_t h,
+                                                  unsigned long long seed) {
+    const unsigned long long n = (unsigned long long)w * h;
+    const unsigned dx = w > 1 ? w - 1 : 1, dy = h > 1 ? h - 1 : 1;
+    const unsigned dxy = (w + h > 2) ? w + h - 2 : 1;
+    for (unsigned long long p = (unsigned long long)blockIdx.x * 256 + threadIdx.x; p < n;
+         p += (unsigned long long)gridDim.x * 256) {
+        const unsigned x = (unsigned)(p % w), y = (unsigned)(p / w);
+        int base[4];
+        base[0] = (int)((unsigned long long)x * 255 / dx);
+        base[1] = (int)((unsigned long long)y * 255 / dy);
+        base[2] = (int)(((unsigned long long)x + y) * 255 / dxy);
+        base[3] = 255 - base[0] / 2;
+        unsigned char v[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int nz = (int)(pl_splitmix64((seed << 40) + p * 4 + c) % 17) - 8;
+            int t = base[c] + nz;
+            t = t < 0 ? 0 : t > 255 ? 255 : t;
+            if (c == 3 && (y / 64) % 4 == 0 && x < w / 16) t = 0;
+            v[c] = (unsigned char)t;
+        }
+        dst[p] = make_uchar4(v[0], v[1], v[2], v[3]);
+    }
+}

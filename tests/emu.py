@@ -1,0 +1,46 @@
+"""ctypes access to tests/simt_emu/libpl_emu.so: the product kernels executed on CPU fibers."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU_DIR = os.path.join(HERE, "simt_emu")
+
+
+class Emu:
+    def __init__(self):
+        subprocess.run(["make", "-s", "-C", EMU_DIR], check=True)
+        self.lib = ctypes.CDLL(os.path.join(EMU_DIR, "libpl_emu.so"))
+        self.lib.emu_optimize.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32,
+                                          ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int,
+                                          ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_void_p]
+        self.lib.emu_optimize.restype = ctypes.c_int
+        self.lib.emu_synth.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
+                                       ctypes.c_uint64]
+        self.lib.emu_synth.restype = None
+
+    def optimize(self, imgs, strength, bleed, adaptive_all, lpc):
+        """imgs: list of equally sized (h, w, 4) uint8 arrays -> dict of outputs."""
+        n = len(imgs)
+        h, w, _ = imgs[0].shape
+        buf = np.ascontiguousarray(np.stack(imgs)).copy()
+        filt = np.zeros((n, h), np.uint8)
+        final = np.zeros((n, 256), np.uint32)
+        status = np.zeros((n, 3), np.uint32)
+        batch = np.zeros(256, np.uint64)
+        chan = np.zeros((n, 5, 4, 256), np.uint32)
+        rc = self.lib.emu_optimize(buf.ctypes.data, n, w, h, filt.ctypes.data, strength, bleed,
+                                   int(adaptive_all), lpc, final.ctypes.data, status.ctypes.data,
+                                   batch.ctypes.data, chan.ctypes.data)
+        assert rc == 0
+        return dict(pixels=buf, filters=filt, final_hist=final, status=status, batch_hist=batch,
+                    chan_hist=chan)
+
+    def synth(self, w, h, seed):
+        a = np.zeros((h, w, 4), np.uint8)
+        self.lib.emu_synth(a.ctypes.data, w, h, seed)
+        return a

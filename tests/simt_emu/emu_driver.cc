@@ -1,0 +1,73 @@
+// TEST INFRASTRUCTURE - runs the product kernels (pngloss_b200/csrc/pl_kernels.cuh, unmodified text)
+// on the CPU SIMT emulator.  Host memory plays the role of device memory.
+#define PL_SIMT_EMU 1
+#include "../../pngloss_b200/csrc/pl_kernels.cuh"
+
+#include <vector>
+
+template <int LPC>
+static void run_k2(const PlImageDev *imgs, const int *slots, int nblocks, int strength, int bleed,
+                   int) {
+    simt::launch([&] { pl_k2_quantize<LPC>(imgs, slots, strength, bleed); },
+                 dim3(nblocks), dim3(PL_K2_THREADS), sizeof(PlCtaSmem<LPC>));
+}
+
+extern "C" int emu_optimize(unsigned char *rgba, int n, uint32_t w, uint32_t h,
+                            unsigned char *filters_out, int strength, int bleed, int adaptive_all,
+                            int lpc, uint32_t *final_hist, uint32_t *status,
+                            unsigned long long *batch_hist, uint32_t *chan_hist_out) {
+    const size_t npx = (size_t)w * h;
+    const size_t ew = (size_t)w + PL_ERR_PAD;
+    std::vector<uchar4> out(npx * n);
+    std::vector<uint32_t> chan(5 * 4 * 256 * (size_t)n, 0), flags(2 * (size_t)n, 0);
+    std::vector<short4> err(2 * 5 * 2 * ew * n);
+    std::vector<uchar4> cand(5 * (size_t)w * n);
+    memset(err.data(), 0x5A, err.size() * sizeof(short4));   // poison: kernel must not rely on zeros
+    memset(cand.data(), 0x5A, cand.size() * sizeof(uchar4));
+    memset(out.data(), 0x5A, out.size() * sizeof(uchar4));
+    std::vector<PlImageDev> imgs(n);
+    for (int i = 0; i < n; i++) {
+        PlImageDev &d = imgs[i];
+        d.in = (const uchar4 *)rgba + npx * i;
+        d.out = out.data() + npx * i;
+        d.filters = filters_out + (size_t)h * i;
+        d.chan_hist = chan.data() + 5 * 4 * 256 * (size_t)i;
+        d.flags = flags.data() + 2 * (size_t)i;
+        d.final_hist = final_hist + 256 * (size_t)i;
+        d.err = err.data() + 2 * 5 * 2 * ew * i;
+        d.cand = cand.data() + 5 * (size_t)w * i;
+        d.status = status + 3 * (size_t)i;
+        d.width = w;
+        d.height = h;
+        d.adaptive_all = adaptive_all > 1 ? (unsigned)((adaptive_all >> (2 + i % 8)) & 1) : (unsigned)adaptive_all;
+        d.force_mode = 0;
+    }
+    const PlImageDev *dimgs = imgs.data();
+    unsigned k1_slices = h < 4 ? h : 4;
+    simt::launch([&] { pl_k1_orig_hist(dimgs, k1_slices); }, dim3(k1_slices * n), dim3(PL_K1_THREADS), 0);
+    if (chan_hist_out) memcpy(chan_hist_out, chan.data(), chan.size() * sizeof(uint32_t));
+
+    const int cpw = 8 / lpc;
+    const int nblocks = (n + cpw - 1) / cpw;
+    std::vector<int> slots((size_t)nblocks * cpw, -1);
+    for (int i = 0; i < n; i++) slots[i] = i;
+    switch (lpc) {
+    case 8: run_k2<8>(dimgs, slots.data(), nblocks, strength, bleed, adaptive_all); break;
+    case 4: run_k2<4>(dimgs, slots.data(), nblocks, strength, bleed, adaptive_all); break;
+    case 2: run_k2<2>(dimgs, slots.data(), nblocks, strength, bleed, adaptive_all); break;
+    case 1: run_k2<1>(dimgs, slots.data(), nblocks, strength, bleed, adaptive_all); break;
+    default: return -1;
+    }
+    if (batch_hist) {
+        memset(batch_hist, 0, 256 * sizeof(unsigned long long));
+        simt::launch([&] { pl_k3_batch_hist(dimgs, n, batch_hist); }, dim3(2), dim3(256), 0);
+    }
+    memcpy(rgba, out.data(), npx * n * sizeof(uchar4));
+    return 0;
+}
+
+extern "C" void emu_synth(unsigned char *dst, uint32_t w, uint32_t h, unsigned long long seed) {
+    simt::launch([&] { pl_k_synth((uchar4 *)dst, w, h, seed); }, dim3(3), dim3(256), 0);
+}
+
+extern "C" unsigned long long emu_collectives() { return simt::n_collectives; }

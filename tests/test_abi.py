@@ -1,0 +1,56 @@
+"""CPU tests of the boundary: the C-ABI library loads without a GPU, exports every symbol that
+include/pngloss_b200.h declares, and refuses to compute without a device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import pngloss_b200
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "pngloss_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = re.findall(r"\b(pngloss_b200_\w+|optimize_with_rows|optimize_with_stride|"
+                       r"optimizeForAverageFilter)\s*\(", text)
+    return sorted(set(names))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    if not os.path.exists(pngloss_b200.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+
+
+def test_header_and_binding_agree():
+    assert declared_symbols() == sorted(pngloss_b200.EXPORTS)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(pngloss_b200.LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(lib, name), name
+
+
+def test_library_has_no_oracle_or_torch_dependency():
+    import subprocess
+    out = subprocess.run(["ldd", pngloss_b200.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "torch" not in out and "pngloss_ref" not in out
+
+
+def test_no_cpu_fallback_without_device():
+    """On a GPU-less host the product must fail loudly instead of computing on the CPU."""
+    if pngloss_b200.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(pngloss_b200.PnglossError):
+        pngloss_b200.Context(0)
+    img = np.full((2, 2, 4), 7, np.uint8)
+    rf = np.zeros(2, np.uint8)
+    rc = pngloss_b200.optimize_with_rows(img, rf, False, 20, 2)
+    assert rc == pngloss_b200.DEVICE_ERROR
+    assert (img == 7).all() and not rf.any()

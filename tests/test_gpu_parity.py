@@ -1,0 +1,251 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Everything goes through the C ABI of
+libpngloss_b200.so; the oracle / golden vectors are only the checker.  Integer path: the bar is
+bit-exact pixels, row filters and histograms."""
+import numpy as np
+import pytest
+
+import pngloss_b200
+from checkers import PNG_MASKS, Oracle, filter_counts, sha16, to_bpp
+from golden_cases import case_id, cases, load_input
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return Oracle()
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = pngloss_b200.Context(0)
+    yield c
+    c.close()
+
+
+def run_dropin(img, s, b, want_filters=True):
+    got = img.copy()
+    rf = np.zeros(img.shape[0], np.uint8) if want_filters else None
+    rc = pngloss_b200.optimize_with_rows(got, rf, False, s, b)
+    assert rc == 0
+    return got, rf
+
+
+# ---- golden vectors produced by the unmodified reference ------------------------------------------
+@pytest.mark.parametrize("c", cases("small", "medium"), ids=case_id)
+def test_golden_through_dropin_entry(oracle, c):
+    img = load_input(c, oracle)
+    assert sha16(img) == c["in_sha"]
+    px, rf = run_dropin(img, c["strength"], c["bleed"], c["filters"])
+    assert sha16(px) == c["px_sha"]
+    if c["filters"]:
+        assert filter_counts(rf) == c["nsuap"]
+        assert sha16(rf) == c["filt_sha"]
+
+
+@pytest.mark.parametrize("lanes", [8, 4, 2, 1])
+def test_golden_batched_all_lane_mappings(ctx, oracle, lanes):
+    """All small golden cases of one (strength, bleed) in a single batch: mixed sizes, mixed colour
+    modes, mixed row_filters/NULL, every lane mapping of the quantise kernel."""
+    ctx.set_lanes(lanes)
+    groups = {}
+    for c in cases("small"):
+        groups.setdefault((c["strength"], c["bleed"]), []).append(c)
+    for (s, b), cs in groups.items():
+        imgs = [load_input(c, oracle).copy() for c in cs]
+        rfs = [np.zeros(im.shape[0], np.uint8) if c["filters"] else None for c, im in zip(cs, imgs)]
+        res = ctx.optimize_batch(imgs, rfs, s, b)
+        for c, im, rf, r in zip(cs, imgs, rfs, res):
+            assert r["status"] == 0
+            assert sha16(im) == c["px_sha"], case_id(c)
+            if c["filters"]:
+                assert sha16(rf) == c["filt_sha"], case_id(c)
+    ctx.set_lanes(0)
+
+
+def test_golden_large_4k_and_1080p(ctx, oracle):
+    """BASELINE configs[2]: 3840x2160 RGBA at strength 0/20/40/85 (+ the 1080p vector), full size,
+    against hashes produced by the reference."""
+    for c in cases("large"):
+        src = c["src"]
+        batch = pngloss_b200.Batch(ctx, [src["w"]], [src["h"]])
+        batch.synth(0, src["seed"])          # device generator == oracle generator (checked below)
+        inp = np.zeros((src["h"], src["w"], 4), np.uint8)
+        batch.download_input(0, inp)
+        batch.run(c["strength"], c["bleed"])
+        st, bpp, retried = batch.finish()
+        out = np.zeros_like(inp)
+        rf = np.zeros(src["h"], np.uint8)
+        batch.download(0, out, rf)
+        ctx.sync()
+        assert sha16(inp) == c["in_sha"], "device generator drifted"
+        assert st[0] == 0 and bpp[0] == 4
+        assert sha16(out) == c["px_sha"], case_id(c)
+        assert sha16(rf) == c["filt_sha"], case_id(c)
+        assert int(batch.image_histogram(0).sum()) == src["w"] * src["h"] * 4
+        batch.close()
+
+
+# ---- fresh inputs against the oracle -----------------------------------------------------------------
+def test_random_inputs_match_oracle(ctx, oracle):
+    rng = np.random.default_rng(424242)
+    for rep in range(6):
+        imgs, params = [], []
+        s = int(rng.choice([0, 1, 7, 19, 20, 40, 85, 200, 255]))
+        b = int(rng.choice([1, 2, 3, 16, 32767]))
+        for i in range(24):
+            w = int(rng.integers(1, 150))
+            h = int(rng.integers(1, 40))
+            kind = i % 3
+            if kind == 0:
+                img = oracle.synth(w, h, 9000 + 100 * rep + i)
+            elif kind == 1:
+                img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+            else:
+                img = (rng.integers(0, 4, (h, w, 4)) * 85).astype(np.uint8)
+            if rng.random() < 0.5:
+                img[rng.random((h, w)) < 0.2, 3] = 0
+            imgs.append(to_bpp(img, int(rng.integers(1, 5))))
+            params.append(bool(rng.random() < 0.7))
+        work = [im.copy() for im in imgs]
+        rfs = [np.zeros(im.shape[0], np.uint8) if nf else None for im, nf in zip(imgs, params)]
+        ctx.set_lanes([8, 4, 2, 1][rep % 4])
+        res = ctx.optimize_batch(work, rfs, s, b)
+        for im, got, rf, nf, r in zip(imgs, work, rfs, params, res):
+            want_px, want_rf, tr = oracle.optimize(im, s, b, nf, trace=True)
+            assert r["status"] == 0
+            assert np.array_equal(got, want_px), (rep, im.shape, s, b, nf)
+            if nf:
+                assert np.array_equal(rf, want_rf), (rep, im.shape, s, b, nf)
+            assert r["retried_rows"] == int((s - tr["row_strength"].astype(int)).sum())
+    ctx.set_lanes(0)
+
+
+def test_retry_path_on_device(ctx, oracle):
+    """row_filters == NULL on tiny noisy images: some rows find no libpng-consistent candidate and are
+    retried at lower strength (reference src/pngloss_image.c:211,273-274)."""
+    rng = np.random.default_rng(7)
+    imgs = [to_bpp(rng.integers(0, 256, (3, 5, 4), dtype=np.uint8), int(rng.integers(1, 5)))
+            for _ in range(64)]
+    for lanes in (8, 1):
+        ctx.set_lanes(lanes)
+        work = [im.copy() for im in imgs]
+        res = ctx.optimize_batch(work, None, 20, 2)
+        total_retries = 0
+        for im, got, r in zip(imgs, work, res):
+            want_px, _, tr = oracle.optimize(im, 20, 2, False, trace=True)
+            assert np.array_equal(got, want_px)
+            assert r["retried_rows"] == int((20 - tr["row_strength"].astype(int)).sum())
+            total_retries += r["retried_rows"]
+        assert total_retries > 0
+    ctx.set_lanes(0)
+
+
+def test_secondary_entry_points(oracle):
+    """optimize_with_stride / optimizeForAverageFilter (reference src/pngloss_image.c:29-50):
+    row_filters == NULL semantics, padded stride."""
+    img = oracle.synth(50, 21, 31)
+    want, _ = oracle.optimize(img, 30, 3, False)
+    padded = np.zeros((21, 64, 4), np.uint8)
+    padded[:, :50] = img
+    view = padded[:, :50]
+    pngloss_b200.optimize_with_stride(view, False, 30, 3)
+    assert np.array_equal(view, want)
+    assert not padded[:, 50:].any()
+    want2, _ = oracle.optimize(img, 25, 2, False)
+    tight = img.copy()
+    pngloss_b200.optimizeForAverageFilter(tight, 25)
+    assert np.array_equal(tight, want2)
+
+
+def test_non_contiguous_row_pointers(oracle):
+    """rows[] need not be equally spaced."""
+    import ctypes
+    img = oracle.synth(40, 10, 77)
+    want_px, want_rf = oracle.optimize(img, 20, 2, True)
+    rows_mem = [np.ascontiguousarray(img[y]).copy() for y in range(10)]
+    order = [3, 7, 1, 9, 0, 5, 2, 8, 6, 4]
+    keep = [rows_mem[i] for i in order]  # scrambles allocation order, not image order
+    ptrs = (ctypes.c_void_p * 10)(*[r.ctypes.data for r in rows_mem])
+    rf = np.zeros(10, np.uint8)
+    lib = pngloss_b200.load_library()
+    assert lib.optimize_with_rows(ptrs, 40, 10, rf.ctypes.data, False, 20, 2) == 0
+    assert np.array_equal(np.stack(rows_mem), want_px) and np.array_equal(rf, want_rf)
+    del keep
+
+
+def test_forced_bytes_per_pixel(ctx, oracle):
+    """The reference's optimize_image takes an explicit bytes_per_pixel (src/pngloss_image.c:159); an
+    opaque gray image forced to gray+alpha must quantise the alpha plane too."""
+    import ctypes
+    img = to_bpp(oracle.synth(33, 9, 5), 1)
+    packed = np.ascontiguousarray(img[:, :, [1, 3]]).reshape(9, 66).copy()
+    rf_want = np.zeros(9, np.uint8)
+    rc = oracle.lib.oracle_optimize_image(packed.ctypes.data, 33, 9, 2, 66, rf_want.ctypes.data, 20, 2,
+                                          None)
+    assert rc == 0
+    got = img.copy()
+    rf = np.zeros(9, np.uint8)
+    res = ctx.optimize_batch([got], [rf], 20, 2, force_bpp=2)
+    assert res[0]["bytes_per_pixel"] == 2
+    assert np.array_equal(got[:, :, 1], packed[:, 0::2]) and np.array_equal(got[:, :, 3], packed[:, 1::2])
+    assert np.array_equal(got[:, :, 0], got[:, :, 1]) and np.array_equal(got[:, :, 2], got[:, :, 1])
+    assert np.array_equal(rf, rf_want)
+
+
+# ---- size-independent properties at full size ------------------------------------------------------
+def test_properties_full_size_batch(ctx, oracle):
+    """8 x 1920x1080 (BASELINE configs[3] shape): strength 0 is the identity; replicas of one image
+    give identical outputs; filters are valid masks; histogram sums; batch histogram = sum."""
+    w, h, n = 1920, 1080, 8
+    batch = pngloss_b200.Batch(ctx, [w] * n, [h] * n)
+    for i in range(n):
+        batch.synth(i, 100 + (i % 2))     # two distinct images, replicated
+    inp = [np.zeros((h, w, 4), np.uint8) for _ in range(2)]
+    batch.download_input(0, inp[0])
+    batch.download_input(1, inp[1])
+    batch.run(0, 2)
+    st, bpp, _ = batch.finish()
+    out = np.zeros((h, w, 4), np.uint8)
+    for i in range(2):
+        batch.download(i, out, None)
+        ctx.sync()
+        assert np.array_equal(out, inp[i]), "strength 0 must be lossless"
+    ctx.set_lanes(4)
+    batch.run(20, 2)
+    st, bpp, _ = batch.finish()
+    assert (st == 0).all() and (bpp == 4).all()
+    outs, rfs = [], []
+    for i in range(n):
+        o = np.zeros((h, w, 4), np.uint8)
+        rf = np.zeros(h, np.uint8)
+        batch.download(i, o, rf)
+        outs.append(o)
+        rfs.append(rf)
+    ctx.sync()
+    golden = [c for c in cases("large") if c["name"] == "synth1920x1080"][0]
+    assert sha16(outs[0]) == golden["px_sha"] and sha16(rfs[0]) == golden["filt_sha"]
+    total = np.zeros(256, np.uint64)
+    for i in range(n):
+        assert np.array_equal(outs[i], outs[i % 2]) and np.array_equal(rfs[i], rfs[i % 2])
+        assert np.isin(rfs[i], PNG_MASKS).all()
+        hist = batch.image_histogram(i)
+        assert int(hist.sum()) == w * h * 4
+        total += hist
+        # fully transparent input pixels stay fully transparent (reference optimize_state.c:158-164)
+        assert (outs[i][..., 3][inp[i % 2][..., 3] == 0] == 0).all()
+    assert np.array_equal(batch.histogram(), total)
+    info = batch.launch_info()
+    assert info["images_per_cta"] == 2 and info["k2_ctas"] == 4
+    ctx.set_lanes(0)
+    batch.close()
+
+
+def test_invalid_arguments(ctx):
+    img = np.zeros((4, 4, 4), np.uint8)
+    with pytest.raises(pngloss_b200.PnglossError):
+        ctx.optimize_batch([img], None, 300, 2)
+    with pytest.raises(pngloss_b200.PnglossError):
+        ctx.optimize_batch([img], None, 20, 0)
+    with pytest.raises(pngloss_b200.PnglossError):
+        pngloss_b200.Batch(ctx, [0], [4])

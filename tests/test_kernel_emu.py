@@ -1,0 +1,116 @@
+"""CPU tests of the *kernel source* (pngloss_b200/csrc/pl_kernels.cuh) executed on the SIMT emulator
+in tests/simt_emu, compared with the oracle.  These check the kernel logic - lane mapping, fix-up
+of the channel order, streamed error windows, histogram-delta cost, winner commit, retry - before any
+GPU time is spent; the parity tests proper are the -m gpu tests that go through the C-ABI."""
+import numpy as np
+import pytest
+
+from checkers import Oracle, to_bpp
+from emu import Emu
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return Emu()
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return Oracle()
+
+
+def compare(emu, oracle, imgs, s, b, null_filters, lpc):
+    got = emu.optimize(imgs, s, b, null_filters, lpc)
+    total = np.zeros(256, np.uint64)
+    for i, img in enumerate(imgs):
+        px, rf, tr = oracle.optimize(img, s, b, not null_filters, trace=True)
+        assert got["status"][i][0] == 0
+        assert np.array_equal(got["pixels"][i], px), f"image {i} pixels"
+        if not null_filters:
+            assert np.array_equal(got["filters"][i], rf), f"image {i} filters"
+        assert np.array_equal(got["final_hist"][i], tr["final_frequency"]), f"image {i} histogram"
+        assert got["status"][i][2] == int((tr["row_strength"] != s).sum() and
+                                          (s - tr["row_strength"].astype(int)).sum())
+        total += tr["final_frequency"]
+    assert np.array_equal(got["batch_hist"], total)
+    return got
+
+
+CASES = [  # w, h, seed, bpp, strength, bleed, null_filters
+    (16, 6, 3, 4, 20, 2, False),
+    (37, 9, 5, 4, 20, 2, False),
+    (64, 7, 7, 3, 20, 2, False),
+    (33, 8, 9, 2, 20, 2, False),
+    (40, 8, 11, 1, 20, 2, False),
+    (35, 7, 13, 4, 85, 1, True),
+    (20, 5, 15, 4, 255, 2, False),
+    (9, 9, 17, 4, 0, 2, False),
+    (1, 1, 3, 4, 20, 2, False),
+    (1, 16, 3, 4, 20, 2, False),
+    (16, 1, 3, 4, 20, 2, False),
+    (31, 4, 19, 4, 5, 32767, False),
+    (66, 3, 21, 2, 40, 3, True),
+]
+
+
+@pytest.mark.parametrize("lpc", [8, 4, 2, 1])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "w%d-h%d-seed%d-bpp%d-s%d-b%d-null%d" % c)
+def test_emu_single_image(emu, oracle, case, lpc):
+    w, h, seed, bpp, s, b, nf = case
+    img = to_bpp(oracle.synth(w, h, seed), bpp)
+    got = compare(emu, oracle, [img], s, b, nf, lpc)
+    assert got["status"][0][1] == bpp or (w * h == 1)
+
+
+@pytest.mark.parametrize("lpc", [8, 4, 2, 1])
+def test_emu_batch_mixed_modes(emu, oracle, lpc):
+    """Several images per CTA (CPW = 8/lpc), every bytes-per-pixel mode, partially filled last CTA."""
+    imgs = [to_bpp(oracle.synth(29, 6, 100 + i), (i % 4) + 1) for i in range(11)]
+    compare(emu, oracle, imgs, 20, 2, False, lpc)
+
+
+@pytest.mark.parametrize("lpc", [8, 2, 1])
+def test_emu_retry_path(emu, oracle, lpc):
+    """row_filters == NULL on tiny noisy images makes the libpng-heuristic check reject all five
+    candidates now and then, which exercises the lower-strength retry (reference
+    src/pngloss_image.c:211,273-274) - in some images of a CTA only."""
+    rng = np.random.default_rng(7)
+    imgs, retried = [], 0
+    while len(imgs) < 16:
+        img = rng.integers(0, 256, (3, 5, 4), dtype=np.uint8)
+        img = to_bpp(img, int(rng.integers(1, 5)))
+        _, _, tr = oracle.optimize(img, 20, 2, False, trace=True)
+        hit = bool((tr["row_strength"] != 20).any())
+        if hit or len(imgs) % 2 == 1:
+            imgs.append(img)
+            retried += hit
+    assert retried >= 6
+    got = compare(emu, oracle, imgs, 20, 2, True, lpc)
+    assert (got["status"][:, 2] > 0).sum() == retried
+
+
+def test_emu_noise_and_ties(emu, oracle):
+    rng = np.random.default_rng(11)
+    few = (rng.integers(0, 4, (6, 21, 4)) * 85).astype(np.uint8)      # few levels: many frequency ties
+    noise = rng.integers(0, 256, (6, 21, 4), dtype=np.uint8)
+    holes = noise.copy()
+    holes[rng.random((6, 21)) < 0.3, 3] = 0                            # fully transparent pixels
+    for lpc in (8, 2):
+        compare(emu, oracle, [few, noise, holes, to_bpp(holes, 2)], 19, 2, False, lpc)
+        compare(emu, oracle, [few, noise, holes, to_bpp(holes, 2)], 200, 1, True, lpc)
+
+
+def test_emu_k1_histograms(emu, oracle):
+    """K1's per-channel histograms, folded by colour mode, equal optimize_state_init's table."""
+    for bpp in (1, 2, 3, 4):
+        img = to_bpp(oracle.synth(23, 11, 40 + bpp), bpp)
+        got = emu.optimize([img], 10, 2, False, 8)
+        chans = {1: [1], 2: [1, 3], 3: [0, 1, 2], 4: [0, 1, 2, 3]}[bpp]
+        folded = got["chan_hist"][0][:, chans, :].sum(axis=1)
+        packed = np.ascontiguousarray(img[:, :, chans]).reshape(img.shape[0], -1)
+        assert np.array_equal(folded, oracle.original_frequency(packed, bpp))
+
+
+def test_emu_synth_matches_oracle(emu, oracle):
+    for (w, h, seed) in [(64, 32, 7), (17, 70, 12345), (1, 1, 3)]:
+        assert np.array_equal(emu.synth(w, h, seed), oracle.synth(w, h, seed))

@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""Tuning sweep (not a bench line): K2 time against images-in-flight and lane mapping.
+Usage: python tools/sweep.py [--width W --height H] --images 148,296 --lanes 8,4,2,1"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import pngloss_b200  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--width", type=int, default=3840)
+    ap.add_argument("--height", type=int, default=2160)
+    ap.add_argument("--images", default="148,296,592")
+    ap.add_argument("--lanes", default="8,4,2,1")
+    ap.add_argument("--strength", type=int, default=20)
+    ap.add_argument("--reps", type=int, default=1)
+    a = ap.parse_args()
+    ctx = pngloss_b200.Context(0)
+    for n in [int(x) for x in a.images.split(",")]:
+        batch = pngloss_b200.Batch(ctx, [a.width] * n, [a.height] * n)
+        for i in range(n):
+            batch.synth(i, 4 + i)
+        ctx.sync()
+        for lanes in [int(x) for x in a.lanes.split(",")]:
+            ctx.set_lanes(lanes)
+            best = None
+            for _ in range(a.reps + 1):       # first run is the warm-up
+                batch.run(a.strength, 2)
+                st, _, _ = batch.finish()
+                assert (st == 0).all()
+                t = batch.timings()
+                if best is None or t["k2_quantize_ms"] < best["k2_quantize_ms"]:
+                    best = t
+            px = n * a.width * a.height
+            print(json.dumps({"images": n, "w": a.width, "h": a.height, "lanes": lanes,
+                              "k1_ms": round(best["k1_hist_ms"], 3), "k2_ms": round(best["k2_quantize_ms"], 3),
+                              "k2_mpx_s": round(px / best["k2_quantize_ms"] / 1e3, 1),
+                              "k1_gpx_s": round(px / best["k1_hist_ms"] / 1e6, 2),
+                              **batch.launch_info()}), flush=True)
+        batch.close()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
