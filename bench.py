@@ -210,15 +210,17 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import pngloss_b200
+    from pngloss_b200.shard import shard_seeds
     ctx = pngloss_b200.Context(local_rank)
     if a.lanes:
         ctx.set_lanes(a.lanes)
     n, w, h = a.images, a.width, a.height
     px_per_step_rank = n * w * h
 
+    seeds = shard_seeds(rank, world, n)        # distinct images on every rank (shards, not replicas)
     batch = pngloss_b200.Batch(ctx, [w] * n, [h] * n)
     for i in range(n):
-        batch.synth(i, 4 + rank * n + i)       # distinct seeds on every rank (shards, not replicas)
+        batch.synth(i, seeds[i])
     ctx.sync()
 
     hist_alias = None
@@ -280,7 +282,7 @@ def main():
         pristine = ctx.pinned_empty((n, h, w, 4))
         b2 = pngloss_b200.Batch(ctx, [w] * n, [h] * n)
         for i in range(n):
-            b2.synth(i, 4 + rank * n + i)
+            b2.synth(i, seeds[i])
             b2.download_input(i, pristine[i])
         ctx.sync()
         b2.close()
