@@ -14,7 +14,8 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpngloss_b200.so")
+# PNGLOSS_B200_LIB selects an alternative build of the same library (tuning experiments only)
+LIB_PATH = os.environ.get("PNGLOSS_B200_LIB") or os.path.join(_HERE, "libpngloss_b200.so")
 
 SUCCESS = 0
 INVALID_ARGUMENT = 4

@@ -334,10 +334,13 @@ static int launch_k2(pngloss_b200_batch *b, int nblocks, unsigned strength, long
     return PNGLOSS_B200_SUCCESS;
 }
 
-// Heuristic until measured otherwise: keep one image per CTA (lowest latency per image) while that
-// already gives every SM several CTAs; pack more images per CTA for very large batches.
+// Lane mapping by batch size, from the B200 sweep in profiles/r1_sweep_lanes.txt (3840-wide images):
+// with few images only wide lane groups keep the SMs busy (one image per CTA); from about four images
+// per SM on, packing 4 images per CTA (2 lanes per channel) issues ~3x fewer instructions per pixel.
 static int choose_lpc(const pngloss_b200_batch *b) {
     if (b->ctx->lpc) return b->ctx->lpc;
+    if (b->n >= 592) return 2;
+    if (b->n >= 296) return 4;
     return 8;
 }
 

@@ -38,6 +38,24 @@ __device__ __forceinline__ int pl_predict(int above, int diag, int left) {
     if (F == 4) return pl_paeth(above, diag, left);
     return 0;
 }
+// Runtime-filter form used by K2: every warp of a CTA runs the same instruction stream (one loop
+// body in the instruction cache instead of five); F is warp-uniform so the paeth branch never diverges.
+struct PlPredictor {
+    int ma, ml, sh;
+    bool paeth;
+};
+__device__ __forceinline__ PlPredictor pl_make_predictor(int F) {
+    PlPredictor p;
+    p.ma = (F == 2 || F == 3) ? 255 : 0;
+    p.ml = (F == 1 || F == 3) ? 255 : 0;
+    p.sh = (F == 3) ? 1 : 0;
+    p.paeth = (F == 4);
+    return p;
+}
+__device__ __forceinline__ int pl_predict_rt(const PlPredictor &p, int above, int diag, int left) {
+    if (p.paeth) return pl_paeth(above, diag, left);
+    return ((above & p.ma) + (left & p.ml)) >> p.sh;
+}
 __device__ __forceinline__ int pl_byte(unsigned v, int c) { return (int)((v >> (8 * c)) & 0xffu); }
 __device__ __forceinline__ unsigned pl_u32(uchar4 p) {
     return (unsigned)p.x | ((unsigned)p.y << 8) | ((unsigned)p.z << 16) | ((unsigned)p.w << 24);
@@ -109,21 +127,33 @@ __global__ void __launch_bounds__(PL_K1_THREADS) pl_k1_orig_hist(const PlImageDe
 // repaired in channel order (see "fix-up" below), which keeps the reference's strictly sequential
 // symbol_frequency semantics while exposing 4-way parallelism.
 // --------------------------------------------------------------------------------------------------
+// Resident CTAs per SM the register allocation of K2 is sized for (5 warps each).  K2 is latency
+// bound (a serial dependency chain per warp), so warps in flight matter more than a few spills.
+#ifndef PL_K2_MIN_BLOCKS
+#define PL_K2_MIN_BLOCKS 4
+#endif
+
 template <int LPC>
 struct PlCfg {
     static const int GROUP = 4 * LPC;    // lanes per chain
     static const int CPW = 32 / GROUP;   // chains per warp = images per CTA
     static const int TP = GROUP;         // pixels per tile per chain (one per lane)
+    // unroll factor of the candidate scan: ceil((strength + 1) / LPC) candidates per lane, i.e. 3, 6,
+    // 11, 21 at the usual strengths 19/20
+    static const int UNR = LPC == 8 ? 3 : LPC == 4 ? 3 : LPC == 2 ? 4 : 7;
+    // bank stagger between the histograms of the chains of one warp (64-bit entries)
+    static const int HPAD = LPC == 2 ? 8 : LPC == 1 ? 4 : 0;
 };
 
 template <int LPC>
 struct PlWarpSmem {
     // input tiles, double buffered; slot 0 of each tile is the last pixel of the previous tile
-    uint32_t orig[2][PlCfg<LPC>::CPW][PlCfg<LPC>::TP + 1];  // original row y
-    uint32_t oa[2][PlCfg<LPC>::CPW][PlCfg<LPC>::TP + 1];    // original row y-1 ("old above")
-    uint32_t na[2][PlCfg<LPC>::CPW][PlCfg<LPC>::TP + 1];    // quantised row y-1 ("new above")
-    short4 e0[2][PlCfg<LPC>::CPW][PlCfg<LPC>::TP];          // incoming error row 0, cells x+4
-    short4 e1[2][PlCfg<LPC>::CPW][PlCfg<LPC>::TP];          // incoming error row 1, cells x+4
+    // (one spare slot at the end of each: the pixel loop fetches one pixel ahead without a bound check)
+    uint32_t orig[2][PlCfg<LPC>::CPW][PlCfg<LPC>::TP + 2];  // original row y
+    uint32_t oa[2][PlCfg<LPC>::CPW][PlCfg<LPC>::TP + 2];    // original row y-1 ("old above")
+    uint32_t na[2][PlCfg<LPC>::CPW][PlCfg<LPC>::TP + 2];    // quantised row y-1 ("new above")
+    short4 e0[2][PlCfg<LPC>::CPW][PlCfg<LPC>::TP + 1];      // incoming error row 0, cells x+4
+    short4 e1[2][PlCfg<LPC>::CPW][PlCfg<LPC>::TP + 1];      // incoming error row 1, cells x+4
     // output staging of the current tile
     uint32_t back[PlCfg<LPC>::CPW][PlCfg<LPC>::TP + 1];     // candidate pixels (slot 0 = carry)
     short4 n0[PlCfg<LPC>::CPW][PlCfg<LPC>::TP];             // finished cells of next error row 0
@@ -132,9 +162,12 @@ struct PlWarpSmem {
 
 template <int LPC>
 struct PlCtaSmem {
-    uint32_t hist[PlCfg<LPC>::CPW][PL_FILTERS][256];  // running symbol histogram of every chain
-    uint32_t base[PlCfg<LPC>::CPW][256];              // histogram at the start of the row
-    uint32_t of[PlCfg<LPC>::CPW][PL_FILTERS][256];    // original_frequency for the image's mode
+    // Per chain and symbol one 64-bit entry that is already most of a candidate key: high word = the
+    // running symbol_frequency, low word = rank of original_frequency[filter][symbol] << 10.
+    // Chains that share a half-warp usually look at the same symbols (residuals cluster at 0), so
+    // consecutive chains are staggered by HPAD entries to land in different banks.
+    unsigned long long hk[PlCfg<LPC>::CPW][PL_FILTERS * 256 + PlCfg<LPC>::HPAD];
+    uint32_t base[PlCfg<LPC>::CPW][256];              // symbol_frequency at the start of the row
     unsigned long long cost[PlCfg<LPC>::CPW][PL_FILTERS];
     PlImageDev img[PlCfg<LPC>::CPW];
     int win[PlCfg<LPC>::CPW];
@@ -167,22 +200,40 @@ __device__ __forceinline__ int pl_chan16(const short4 &v, int c) {
     return ((const short *)&v)[c];
 }
 
-template <int LPC, int F>
-__device__ __noinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC> &sm, const PlChain &cn, int W,
-                                                       int y, int parity, int prev_w, bool adaptive,
-                                                       unsigned bleed_magic) {
+// Candidate key, one 64-bit word whose plain unsigned maximum is the reference's choice
+// (src/optimize_state.c:212-244):
+//   [63:32] symbol_frequency of the candidate
+//   [31:10] rank of original_frequency[filter][symbol] among the 256 symbols (order preserving, so
+//           comparing ranks == comparing the 31-bit counts; built once per image in the prologue)
+//   [9]     symbol == exact (unquantised) symbol
+//   [8:0]   511 - offset of the symbol in its band: earlier candidates win ties, and keys are unique
+// 0 = "no candidate" (every real key has a non-zero low field).
+#define PL_KEY_RANK_SHIFT 10
+__device__ __forceinline__ unsigned pl_key_low(bool exact, int pos) {
+    return ((unsigned)exact << 9) | (unsigned)(511 - pos);
+}
+#define PL_KEY_RANK_MASK (~((1ull << PL_KEY_RANK_SHIFT) - 1ull))   /* count + rank fields */
+
+template <int LPC>
+__device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC> &sm, const PlChain &cn, int F,
+                                                          int W, int y, int parity, int prev_w,
+                                                          bool adaptive, unsigned bleed_magic) {
     typedef PlCfg<LPC> C;
     const int lane = threadIdx.x & 31;
     const int ci = lane / C::GROUP, gl = lane % C::GROUP;
     const int ch = gl / LPC, sub = gl % LPC;
     PlWarpSmem<LPC> &ws = sm.w[F];
-    uint32_t *hist = sm.hist[ci][F];
-    const uint32_t *of = sm.of[ci][F];
+    unsigned long long *hk = &sm.hk[ci][F * 256];
     const int EW = W + PL_ERR_PAD;
     const bool live = cn.live;
     const bool first = (y == 0);
-    const bool act = live && ((cn.chmask >> ch) & 1);
+    const int chmask = cn.chmask;
+    const bool gray = cn.gray, alpha_rule = cn.alpha_rule;
+    const unsigned step_magic = cn.step_magic;
+    const bool act = live && ((chmask >> ch) & 1);
     const int q = cn.q, step = cn.q + 1;
+    const int jmax = (q + LPC) / LPC;   // ceil((q + 1) / LPC)
+    const PlPredictor predictor = pl_make_predictor(F);
 
     const short4 *Ecur0 = cn.err + ((size_t)(parity * PL_FILTERS + prev_w) * 2 + 0) * EW;
     const short4 *Ecur1 = Ecur0 + EW;
@@ -239,83 +290,114 @@ __device__ __noinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC> &sm, const
         const int npx = min(C::TP, W - x0);
         if (t + 1 < ntiles) issue(t + 1, buf ^ 1);
 
+        // this lane's channel of the tile's first pixel; later pixels are fetched one iteration ahead
+        int o_n = ((const unsigned char *)&ws.orig[buf][ci][1])[ch];
+        int a_n = ((const unsigned char *)&ws.na[buf][ci][1])[ch];
+        int e0_n = pl_chan16(ws.e0[buf][ci][0], ch);
+        int e1_n = pl_chan16(ws.e1[buf][ci][0], ch);
         for (int i = 0; i < npx; i++) {
-            // ---- fetch this lane's channel of pixel x0+i -------------------------------------
-            const int o = ((const unsigned char *)&ws.orig[buf][ci][i + 1])[ch];
-            const int a = ((const unsigned char *)&ws.na[buf][ci][i + 1])[ch];
-            a2 = pl_chan16(ws.e0[buf][ci][i], ch);
-            b4 = pl_chan16(ws.e1[buf][ci][i], ch);
+            const int o = o_n, a = a_n;
+            a2 = e0_n;
+            b4 = e1_n;
             c3 = 0;
-            int pred = pl_predict<F>(a, aprev, left);
-            const bool transp = cn.alpha_rule && ch == 3 && o == 0;
+            // prefetch pixel i+1, off the dependency chain (the slot after the tile is a spare)
+            o_n = ((const unsigned char *)&ws.orig[buf][ci][i + 2])[ch];
+            a_n = ((const unsigned char *)&ws.na[buf][ci][i + 2])[ch];
+            e0_n = pl_chan16(ws.e0[buf][ci][i + 1], ch);
+            e1_n = pl_chan16(ws.e1[buf][ci][i + 1], ch);
+            int pred = pl_predict_rt(predictor, a, aprev, left);
+            const bool transp = alpha_rule && ch == 3 && o == 0;
 
             // ---- band of admissible symbols (reference src/optimize_state.c:158-210) ---------
-            int here, lo, hi, ex;
-            if (transp) {
+            // wrap (:175-182): bring the exact symbol orig - predicted into [-128, 127]
+            int ex = o - pred;
+            const int adj = ex < -128 ? -256 : (ex > 127 ? 256 : 0);
+            pred += adj;
+            ex -= adj;
+            // band (:186-193): the multiple-of-(q+1) bucket that holds want, away from zero
+            int here = o + pl_sext16(a0);
+            const int want = here - pred;
+            const unsigned m = (unsigned)(want < 0 ? -want : want);
+            const int r = (int)(m - pl_udiv_magic(m, step_magic) * (unsigned)step);
+            int lo = want + (want < 0 ? r - q : -r);
+            int hi = lo + q;
+            // clamp (:195-210): symbol + predicted must be a byte.  The reference clamps lo from below
+            // and hi from above and collapses an emptied band onto the saturated value, which is the
+            // same as clamping both ends to [-predicted, 255 - predicted].
+            const int smin = -pred, smax = 255 - pred;
+            lo = min(max(lo, smin), smax);
+            hi = min(max(hi, smin), smax);
+            if (transp) {   // fully transparent stays transparent (:158-164): the only symbol is 0 - predicted
                 here = 0;
-                lo = hi = ex = -pred;
-            } else {
-                here = o + pl_sext16(a0);
-                ex = o - pred;
-                if (ex < -128) { pred -= 256; ex += 256; }
-                else if (ex > 127) { pred += 256; ex -= 256; }
-                const int want = here - pred;
-                const unsigned m = (unsigned)(want < 0 ? -want : want);
-                const int r = (int)(m - pl_udiv_magic(m, cn.step_magic) * (unsigned)step);
-                if (want < 0) { hi = -((int)m - r); lo = hi - q; }
-                else { lo = want - r; hi = lo + q; }
-                if (lo + pred < 0) lo = -pred;
-                if (hi + pred > 255) hi = 255 - pred;
-                if (hi < lo) {
-                    if (want + pred > 255) lo = hi = 255 - pred;
-                    if (want + pred < 0) lo = hi = -pred;
-                }
+                lo = hi = ex = smin;
             }
             const int span = act ? hi - lo : -1;
 
             // ---- candidate scan against the histogram at the start of the pixel ---------------
-            // key = (symbol_frequency, original_frequency, symbol == exact), earliest symbol wins
-            // ties (reference :212-244).
+            // Every lane looks at candidates sub, sub + LPC, ...; the trip count comes from the
+            // strength (warp-uniform), candidates beyond the clamped band are predicated off, and the
+            // body is unrolled so that the independent shared-memory loads are in flight together.
             unsigned long long bkey = 0;
-            int bpos = 0x7fff;
-            for (int pos = sub; pos <= span; pos += LPC) {
-                const int s = lo + pos;
-                const unsigned idx = (unsigned)s & 255u;
-                const unsigned long long key = ((unsigned long long)hist[idx] << 32) |
-                                               (unsigned long long)((of[idx] << 1) | (unsigned)(s == ex));
-                if (key > bkey || bpos == 0x7fff) { bkey = key; bpos = pos; }
+            for (int j0 = 0; j0 < jmax; j0 += C::UNR) {
+#pragma unroll
+                for (int u = 0; u < C::UNR; u++) {
+                    const int pos = sub + (j0 + u) * LPC;
+                    const int s = lo + pos;
+                    const unsigned long long key = hk[(unsigned)s & 255u] | pl_key_low(s == ex, pos);
+                    bkey = (pos <= span && key > bkey) ? key : bkey;
+                }
             }
 #pragma unroll
             for (int mk = 1; mk < LPC; mk <<= 1) {
                 const unsigned long long okey = __shfl_xor_sync(PL_FULL, bkey, mk);
-                const int opos = __shfl_xor_sync(PL_FULL, bpos, mk);
-                if (okey > bkey || (okey == bkey && opos < bpos)) { bkey = okey; bpos = opos; }
+                bkey = okey > bkey ? okey : bkey;
             }
-            unsigned bf = (unsigned)(bkey >> 32), bk2 = (unsigned)bkey;
+            int bpos = 511 - (int)((unsigned)bkey & 511u);
 
             // ---- fix-up: replay the channel order ---------------------------------------------
             // The reference increments symbol_frequency[best] before the next channel looks at it
             // (:253).  Raising one count can only promote that one symbol, so the true winner of
             // channel k is either its provisional winner or one of the symbols chosen by channels
             // 0..k-1 (with their counts as updated so far).
+            //
+            // Fast path: a symbol v chosen by an earlier channel can only overtake this channel's
+            // winner if v lies in this band, is not the winner itself, and count[v] + (at most 3
+            // increments) reaches the winner's count.  If that holds nowhere in the warp, every
+            // provisional winner is final (induction over the channel order).  The test needs only
+            // provisional values, so its three steps are independent of each other.
+            bool conflict = false;
+            {
+                const int bsym = lo + bpos;
+                const unsigned bf = (unsigned)(bkey >> 32);
 #pragma unroll
-            for (int t2 = 0; t2 < 3; t2++) {
-                const int src = ci * C::GROUP + t2 * LPC;
-                const int vsym = __shfl_sync(PL_FULL, lo + bpos, src);
-                const unsigned fv = __shfl_sync(PL_FULL, bf, src);
-                const unsigned kv = __shfl_sync(PL_FULL, bk2, src);
-                if (ch > t2 && act && ((cn.chmask >> t2) & 1)) {
+                for (int t2 = 0; t2 < 3; t2++) {
+                    const int src = ci * C::GROUP + t2 * LPC;
+                    const int vsym = __shfl_sync(PL_FULL, bsym, src);
+                    const unsigned fv = __shfl_sync(PL_FULL, bf, src);
                     const int pos = (vsym - lo) & 255;
-                    if (pos <= span) {
-                        if (pos == bpos) {
-                            bf += 1;
-                        } else {
-                            const unsigned f2 = fv + 1;
-                            const unsigned k2 = (kv & ~1u) | (unsigned)(lo + pos == ex);
-                            if (f2 > bf || (f2 == bf && (k2 > bk2 || (k2 == bk2 && pos < bpos)))) {
-                                bf = f2;
-                                bk2 = k2;
-                                bpos = pos;
+                    conflict |= (ch > t2) & act & (bool)((chmask >> t2) & 1) & (pos <= span) &
+                                (pos != bpos) & (fv + 3u >= bf);
+                }
+            }
+            if (__any_sync(PL_FULL, conflict)) {
+                // Slow path (rare once counts have spread): the exact sequential replay.
+#pragma unroll
+                for (int t2 = 0; t2 < 3; t2++) {
+                    const int src = ci * C::GROUP + t2 * LPC;
+                    const int vsym = __shfl_sync(PL_FULL, lo + bpos, src);
+                    const unsigned long long kv = __shfl_sync(PL_FULL, bkey, src);
+                    if (ch > t2 && act && ((chmask >> t2) & 1)) {
+                        const int pos = (vsym - lo) & 255;
+                        if (pos <= span) {
+                            if (pos == bpos) {
+                                bkey += 1ull << 32;          // my own winner was chosen again: count + 1
+                            } else {
+                                const unsigned long long key =
+                                    ((kv & PL_KEY_RANK_MASK) + (1ull << 32)) | pl_key_low(lo + pos == ex, pos);
+                                if (key > bkey) {
+                                    bkey = key;
+                                    bpos = pos;
+                                }
                             }
                         }
                     }
@@ -326,7 +408,7 @@ __device__ __noinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC> &sm, const
             const int sym = lo + bpos;
             const int back = act ? sym + pred : 0;
             if (act && sub == 0) {
-                atomicAdd(&hist[(unsigned)sym & 255u], 1u);
+                atomicAdd((unsigned *)&hk[(unsigned)sym & 255u] + 1, 1u);   // high word = count
                 ((unsigned char *)&ws.back[ci][i + 1])[ch] = (unsigned char)back;
             }
             left = back;
@@ -382,13 +464,13 @@ __device__ __noinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC> &sm, const
             unsigned e = 0;
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                if ((cn.chmask >> c) & 1) {
+                if ((chmask >> c) & 1) {
                     const int oc = pl_byte(o4, c), qc = pl_byte(q4, c);
                     const int da = (pl_byte(oa4, c) - oc) - (pl_byte(na4, c) - qc);
                     const int dg = (pl_byte(oad4, c) - oc) - (pl_byte(nad4, c) - qc);
                     const int dl = (pl_byte(ol4, c) - oc) - (pl_byte(ql4, c) - qc);
                     const unsigned s2 = (unsigned)(da * da + dg * dg + dl * dl);
-                    e += (cn.gray && c == 1) ? 3u * s2 : s2;
+                    e += (gray && c == 1) ? 3u * s2 : s2;
                     if (adaptive) {
                         const int lq = pl_byte(ql4, c), aq = pl_byte(na4, c), dq = pl_byte(nad4, c);
                         as0 += pl_absres(qc, 0);
@@ -428,7 +510,7 @@ __device__ __noinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC> &sm, const
     // ulog2(UINTMAX_MAX / f) == 33 + clz32(f) for every f >= 1.
     unsigned bits = 0;
     for (int s = gl; s < 256; s += C::GROUP) {
-        const unsigned hv = hist[s];
+        const unsigned hv = (unsigned)(hk[s] >> 32);
         bits += (hv - sm.base[ci][s]) * (33u + (unsigned)__clz((int)hv));
     }
 #pragma unroll
@@ -455,7 +537,7 @@ __device__ __noinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC> &sm, const
 }
 
 template <int LPC>
-__global__ void __launch_bounds__(PL_K2_THREADS)
+__global__ void __launch_bounds__(PL_K2_THREADS, PL_K2_MIN_BLOCKS)
 pl_k2_quantize(const PlImageDev *imgs, const int *slots, int strength, int bleed) {
     typedef PlCfg<LPC> C;
     PL_DYN_SMEM(smem_raw);
@@ -491,6 +573,7 @@ pl_k2_quantize(const PlImageDev *imgs, const int *slots, int strength, int bleed
         cn.q = strength;
         cn.step_magic = pl_make_magic((unsigned)strength + 1u);
     }
+    // original_frequency of the image's colour mode (K1 counted every RGBA channel separately) ...
     for (int k = tid; k < C::CPW * PL_FILTERS * 256; k += PL_K2_THREADS) {
         const int c2 = k / (PL_FILTERS * 256), r = k % (PL_FILTERS * 256);
         const int f = r / 256, s = r % 256;
@@ -500,9 +583,31 @@ pl_k2_quantize(const PlImageDev *imgs, const int *slots, int strength, int bleed
 #pragma unroll
         for (int c = 0; c < 4; c++)
             if ((mask >> c) & 1) v += im.chan_hist[(f * 4 + c) * 256 + s];
-        sm.of[c2][f][s] = v;
-        sm.hist[c2][f][s] = 0;
-        if (f == 0) sm.base[c2][s] = 0;
+        sm.hk[c2][f * 256 + s] = v;      // staged in the low word, replaced by its rank below
+    }
+    __syncthreads();
+    // ... enters the candidate key only as a tie-break, so an order-preserving rank is enough:
+    // rank = number of symbols with a strictly smaller count (equal counts share a rank).
+    unsigned my_rank[(PlCfg<LPC>::CPW * PL_FILTERS * 256 + PL_K2_THREADS - 1) / PL_K2_THREADS];
+    {
+        int n = 0;
+        for (int k = tid; k < C::CPW * PL_FILTERS * 256; k += PL_K2_THREADS, n++) {
+            const int c2 = k / (PL_FILTERS * 256), r = k % (PL_FILTERS * 256);
+            const int f = r / 256, s = r % 256;
+            const unsigned mine = (unsigned)sm.hk[c2][f * 256 + s];
+            unsigned rank = 0;
+            for (int s2 = 0; s2 < 256; s2++) rank += (unsigned)((unsigned)sm.hk[c2][f * 256 + s2] < mine);
+            my_rank[n] = rank;
+        }
+    }
+    __syncthreads();
+    {
+        int n = 0;
+        for (int k = tid; k < C::CPW * PL_FILTERS * 256; k += PL_K2_THREADS, n++) {
+            const int c2 = k / (PL_FILTERS * 256), r = k % (PL_FILTERS * 256);
+            sm.hk[c2][r] = (unsigned long long)(my_rank[n] << PL_KEY_RANK_SHIFT);  // count 0
+            if (r < 256) sm.base[c2][r] = 0;
+        }
     }
     __syncthreads();
 
@@ -518,14 +623,8 @@ pl_k2_quantize(const PlImageDev *imgs, const int *slots, int strength, int bleed
         cn.live = valid && !failed;
         bool pending = cn.live;
         for (;;) {
-            unsigned long long cost;
-            switch (F) {
-            case 0: cost = pl_row_pass<LPC, 0>(sm, cn, W, y, y & 1, prev_w, adaptive, bleed_magic); break;
-            case 1: cost = pl_row_pass<LPC, 1>(sm, cn, W, y, y & 1, prev_w, adaptive, bleed_magic); break;
-            case 2: cost = pl_row_pass<LPC, 2>(sm, cn, W, y, y & 1, prev_w, adaptive, bleed_magic); break;
-            case 3: cost = pl_row_pass<LPC, 3>(sm, cn, W, y, y & 1, prev_w, adaptive, bleed_magic); break;
-            default: cost = pl_row_pass<LPC, 4>(sm, cn, W, y, y & 1, prev_w, adaptive, bleed_magic); break;
-            }
+            const unsigned long long cost =
+                pl_row_pass<LPC>(sm, cn, F, W, y, y & 1, prev_w, adaptive, bleed_magic);
             if (gl == 0 && cn.live) sm.cost[ci][F] = cost;
             __syncthreads();
 
@@ -564,10 +663,10 @@ pl_k2_quantize(const PlImageDev *imgs, const int *slots, int strength, int bleed
                         dst[x] = p;
                     }
                     for (int s = tid; s < 256; s += PL_K2_THREADS) {
-                        const unsigned v = sm.hist[c2][w2][s];
+                        const unsigned v = (unsigned)(sm.hk[c2][w2 * 256 + s] >> 32);
                         sm.base[c2][s] = v;
 #pragma unroll
-                        for (int f = 0; f < PL_FILTERS; f++) sm.hist[c2][f][s] = v;
+                        for (int f = 0; f < PL_FILTERS; f++) ((unsigned *)&sm.hk[c2][f * 256 + s])[1] = v;
                     }
                     if (tid == 0) im.filters[y] = (unsigned char)(0x08 << w2);
                 } else {
@@ -575,7 +674,7 @@ pl_k2_quantize(const PlImageDev *imgs, const int *slots, int strength, int bleed
                     for (int s = tid; s < 256; s += PL_K2_THREADS) {
                         const unsigned v = sm.base[c2][s];
 #pragma unroll
-                        for (int f = 0; f < PL_FILTERS; f++) sm.hist[c2][f][s] = v;
+                        for (int f = 0; f < PL_FILTERS; f++) ((unsigned *)&sm.hk[c2][f * 256 + s])[1] = v;
                     }
                 }
             }

@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <map>
 #include <vector>
 
 struct uchar4 { unsigned char x, y, z, w; };
@@ -47,11 +48,15 @@ static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) {
 namespace simt {
 
 struct Fiber;
-struct WarpState {
+// One rendezvous slot per member mask, so that disjoint lane groups of one warp can sit in different
+// collectives at the same time (e.g. redux.sync over 8-lane groups with four different masks).
+struct Slot {
     unsigned arrived = 0;
     unsigned gen = 0;
     unsigned long long val[2][32];
-    unsigned pred_result[2];
+};
+struct WarpState {
+    std::map<unsigned, Slot> slots;
 };
 struct BlockState {
     unsigned nthreads = 0;
@@ -83,7 +88,7 @@ static inline WarpState &my_warp() { return blk.warps[cur->tid.x >> 5]; }
 
 // Generic warp rendezvous: every lane in `mask` deposits v, then all proceed with a snapshot.
 static inline const unsigned long long *rendezvous(unsigned mask, unsigned long long v) {
-    WarpState &w = my_warp();
+    Slot &w = my_warp().slots[mask];
     unsigned lane = lane_id();
     if (!(mask >> lane & 1u)) { fprintf(stderr, "simt_emu: lane %u not in mask %08x\n", lane, mask); abort(); }
     unsigned g = w.gen;
