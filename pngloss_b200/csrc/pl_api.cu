@@ -319,7 +319,7 @@ template <int LPC>
 static int launch_k2(pngloss_b200_batch *b, int nblocks, unsigned strength, long bleed) {
     pngloss_b200_ctx *ctx = b->ctx;
     static bool attr_set[16] = {false};
-    const size_t smem = sizeof(PlCtaSmem<LPC>);
+    const size_t smem = sizeof(PlCtaSmem<LPC>) + PL_K2_SMEM_ALIGN;   // slack for the in-kernel alignment
     if (!attr_set[ctx->device & 15]) {
         PL_CUDA(ctx, cudaFuncSetAttribute(pl_k2_quantize<LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem));

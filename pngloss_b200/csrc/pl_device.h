@@ -44,6 +44,39 @@ __device__ __forceinline__ void pl_cp_async_wait_all() {
 #endif
 }
 
+// round a dynamic shared memory pointer up to `align` bytes (power of two) in the shared address space
+__device__ __forceinline__ unsigned char *pl_align_shared(unsigned char *p, unsigned align) {
+#ifdef PL_SIMT_EMU
+    return (unsigned char *)(((uintptr_t)p + align - 1) & ~(uintptr_t)(align - 1));
+#else
+    const unsigned s = (unsigned)__cvta_generic_to_shared(p);
+    return p + ((align - (s & (align - 1))) & (align - 1));
+#endif
+}
+
+// ---- 2 KB-aligned shared-memory table of 256 64-bit entries -------------------------------------------
+// The candidate scan of K2 reads entry ((first + k * step) mod 256) many times per pixel.  With the table
+// 2 KB aligned the address is base | (byte_offset & 0x7f8): one LOP3 instead of a multiply-add chain.
+#ifdef PL_SIMT_EMU
+struct PlHkTable { const unsigned long long *p; };
+__device__ __forceinline__ PlHkTable pl_hk_table(const unsigned long long *tab) { return PlHkTable{tab}; }
+__device__ __forceinline__ unsigned long long pl_hk_load(PlHkTable t, unsigned byteoff) {
+    return t.p[(byteoff & 0x7f8u) >> 3];
+}
+#else
+struct PlHkTable { unsigned saddr; };
+__device__ __forceinline__ PlHkTable pl_hk_table(const unsigned long long *tab) {
+    PlHkTable t;
+    t.saddr = (unsigned)__cvta_generic_to_shared(tab);
+    return t;
+}
+__device__ __forceinline__ unsigned long long pl_hk_load(PlHkTable t, unsigned byteoff) {
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(t.saddr | (byteoff & 0x7f8u)) : "memory");
+    return v;
+}
+#endif
+
 // ---- exact small-integer division by a runtime constant -------------------------------------------
 // n / d for 0 <= n < 2^17, 1 <= d < 2^15, with magic = floor(2^32 / d) + 1 precomputed (d >= 2).
 // Error bound: n * (magic*d - 2^32) <= n * d < 2^32, so the high word is exactly floor(n / d).

@@ -129,8 +129,10 @@ __global__ void __launch_bounds__(PL_K1_THREADS) pl_k1_orig_hist(const PlImageDe
 // --------------------------------------------------------------------------------------------------
 // Resident CTAs per SM the register allocation of K2 is sized for (5 warps each).  K2 is latency
 // bound (a serial dependency chain per warp), so warps in flight matter more than a few spills.
+// Shared memory already caps the narrow-lane variants at 3 (LPC 2) and 2 (LPC 1) CTAs per SM, so they
+// may use more registers - spent on unrolling the candidate scan for instruction-level parallelism.
 #ifndef PL_K2_MIN_BLOCKS
-#define PL_K2_MIN_BLOCKS 4
+#define PL_K2_MIN_BLOCKS(LPC) ((LPC) >= 4 ? 4 : (LPC) == 2 ? 3 : 2)
 #endif
 
 template <int LPC>
@@ -140,9 +142,14 @@ struct PlCfg {
     static const int TP = GROUP;         // pixels per tile per chain (one per lane)
     // unroll factor of the candidate scan: ceil((strength + 1) / LPC) candidates per lane, i.e. 3, 6,
     // 11, 21 at the usual strengths 19/20
-    static const int UNR = LPC == 8 ? 3 : LPC == 4 ? 3 : LPC == 2 ? 4 : 7;
-    // bank stagger between the histograms of the chains of one warp (64-bit entries)
-    static const int HPAD = LPC == 2 ? 8 : LPC == 1 ? 4 : 0;
+    static const int UNR = LPC == 8 ? 3 : LPC == 4 ? 3 : 11;
+    static const bool DUAL = LPC <= 2;   // two running maxima in the scan (latency-bound variants)
+    static const int LOG2LPC = LPC == 8 ? 3 : LPC == 4 ? 2 : LPC == 2 ? 1 : 0;
+    // narrow lane groups scan many candidates per lane: test the one "exact" candidate separately
+    // instead of carrying its flag through every candidate
+    static const bool EXSEP = LPC <= 2;
+    // bank stagger between the histograms of the chains of one warp (64-bit entries, rotation)
+    static const int HROT = LPC == 2 ? 8 : LPC == 1 ? 4 : 0;
 };
 
 template <int LPC>
@@ -160,13 +167,16 @@ struct PlWarpSmem {
     short4 n1[PlCfg<LPC>::CPW][PlCfg<LPC>::TP];             // finished cells of next error row 1
 };
 
+#define PL_K2_SMEM_ALIGN 2048
+
 template <int LPC>
 struct PlCtaSmem {
     // Per chain and symbol one 64-bit entry that is already most of a candidate key: high word = the
     // running symbol_frequency, low word = rank of original_frequency[filter][symbol] << 10.
-    // Chains that share a half-warp usually look at the same symbols (residuals cluster at 0), so
-    // consecutive chains are staggered by HPAD entries to land in different banks.
-    unsigned long long hk[PlCfg<LPC>::CPW][PL_FILTERS * 256 + PlCfg<LPC>::HPAD];
+    // Must stay the first member: every 256-entry table is then 2 KB aligned (see pl_hk_load).
+    // Chains that share a half-warp usually look at the same symbols (residuals cluster at 0), so the
+    // table of chain ci is stored rotated by ci * HROT entries to land in different banks.
+    unsigned long long hk[PlCfg<LPC>::CPW][PL_FILTERS * 256];
     uint32_t base[PlCfg<LPC>::CPW][256];              // symbol_frequency at the start of the row
     unsigned long long cost[PlCfg<LPC>::CPW][PL_FILTERS];
     PlImageDev img[PlCfg<LPC>::CPW];
@@ -224,16 +234,21 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC> &sm, co
     const int ch = gl / LPC, sub = gl % LPC;
     PlWarpSmem<LPC> &ws = sm.w[F];
     unsigned long long *hk = &sm.hk[ci][F * 256];
+    const PlHkTable hkt = pl_hk_table(hk);
+    const int rot = ci * C::HROT;        // physical entry of symbol s is (s + rot) & 255
     const int EW = W + PL_ERR_PAD;
     const bool live = cn.live;
     const bool first = (y == 0);
     const int chmask = cn.chmask;
-    const bool gray = cn.gray, alpha_rule = cn.alpha_rule;
+    const bool alpha_rule = cn.alpha_rule;
     const unsigned step_magic = cn.step_magic;
     const bool act = live && ((chmask >> ch) & 1);
     const int q = cn.q, step = cn.q + 1;
     const int jmax = (q + LPC) / LPC;   // ceil((q + 1) / LPC)
     const PlPredictor predictor = pl_make_predictor(F);
+    // byte selector that brings a pixel word into the mode's canonical form (byte 4 = zero):
+    // rgba: as is; rgb: alpha -> 0; gray+alpha: G,G,G,A; gray: G,G,G,0
+    const unsigned canon = chmask == 0xF ? 0x3210u : chmask == 0x7 ? 0x4210u : chmask == 0xA ? 0x3111u : 0x4111u;
 
     const short4 *Ecur0 = cn.err + ((size_t)(parity * PL_FILTERS + prev_w) * 2 + 0) * EW;
     const short4 *Ecur1 = Ecur0 + EW;
@@ -337,15 +352,35 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC> &sm, co
             // Every lane looks at candidates sub, sub + LPC, ...; the trip count comes from the
             // strength (warp-uniform), candidates beyond the clamped band are predicated off, and the
             // body is unrolled so that the independent shared-memory loads are in flight together.
-            unsigned long long bkey = 0;
-            for (int j0 = 0; j0 < jmax; j0 += C::UNR) {
+            unsigned long long bkey = 0, bkey2 = 0;   // two running maxima: shorter dependency chain
+            {
+                const int jl = (span - sub) >> C::LOG2LPC;          // last valid j of this lane (-1: none)
+                const unsigned off0 = (unsigned)(lo + sub + rot) * 8u;   // byte offset of candidate j = 0
+                const unsigned low0 = 511u - (unsigned)sub;          // its "511 - pos" field
+                const int jx = ex - lo - sub;                        // j * LPC of the exact symbol, if mine
+                for (int j0 = 0; j0 < jmax; j0 += C::UNR) {
+                    // per-chunk bases, so that each candidate below only adds compile-time constants
+                    const unsigned off_c = off0 + (unsigned)(j0 * LPC * 8);
+                    const unsigned low_c = low0 - (unsigned)(j0 * LPC);
+                    const int jl_c = jl - j0, jx_c = jx - j0 * LPC;
 #pragma unroll
-                for (int u = 0; u < C::UNR; u++) {
-                    const int pos = sub + (j0 + u) * LPC;
-                    const int s = lo + pos;
-                    const unsigned long long key = hk[(unsigned)s & 255u] | pl_key_low(s == ex, pos);
-                    bkey = (pos <= span && key > bkey) ? key : bkey;
+                    for (int u = 0; u < C::UNR; u++) {
+                        unsigned long long key = pl_hk_load(hkt, off_c + (unsigned)(u * LPC * 8));
+                        key |= low_c - (unsigned)(u * LPC);          // low 10 bits of an entry are zero
+                        if (!C::EXSEP) key |= (unsigned)(u * LPC == jx_c) << 9;
+                        if (C::DUAL && (u & 1)) bkey2 = (u <= jl_c && key > bkey2) ? key : bkey2;
+                        else bkey = (u <= jl_c && key > bkey) ? key : bkey;
+                    }
                 }
+                if (C::EXSEP) {
+                    // the exact symbol, with its bonus bit; every lane of the group may add it (max is
+                    // idempotent)
+                    const int pos = ex - lo;
+                    const unsigned long long key =
+                        pl_hk_load(hkt, (unsigned)(ex + rot) * 8u) | pl_key_low(true, pos & 255);
+                    bkey2 = (pos >= 0 && pos <= span && key > bkey2) ? key : bkey2;
+                }
+                if (C::DUAL || C::EXSEP) bkey = bkey2 > bkey ? bkey2 : bkey;
             }
 #pragma unroll
             for (int mk = 1; mk < LPC; mk <<= 1) {
@@ -367,21 +402,21 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC> &sm, co
             // provisional values, so its three steps are independent of each other.
             bool conflict = false;
             {
-                const int bsym = lo + bpos;
-                const unsigned bf = (unsigned)(bkey >> 32);
+                // one word per channel group: winner's count (saturated to 24 bits, which only makes the
+                // test more conservative) and its symbol
+                const unsigned bf = min((unsigned)(bkey >> 32), 0xfffff0u);
+                const unsigned mine = (bf << 8) | ((unsigned)(lo + bpos) & 255u);
 #pragma unroll
                 for (int t2 = 0; t2 < 3; t2++) {
-                    const int src = ci * C::GROUP + t2 * LPC;
-                    const int vsym = __shfl_sync(PL_FULL, bsym, src);
-                    const unsigned fv = __shfl_sync(PL_FULL, bf, src);
-                    const int pos = (vsym - lo) & 255;
+                    const unsigned theirs = __shfl_sync(PL_FULL, mine, ci * C::GROUP + t2 * LPC);
+                    const int pos = ((int)(theirs & 255u) - lo) & 255;
                     conflict |= (ch > t2) & act & (bool)((chmask >> t2) & 1) & (pos <= span) &
-                                (pos != bpos) & (fv + 3u >= bf);
+                                (pos != bpos) & ((theirs >> 8) + 3u >= bf);
                 }
             }
             if (__any_sync(PL_FULL, conflict)) {
                 // Slow path (rare once counts have spread): the exact sequential replay.
-#pragma unroll
+#pragma unroll 1
                 for (int t2 = 0; t2 < 3; t2++) {
                     const int src = ci * C::GROUP + t2 * LPC;
                     const int vsym = __shfl_sync(PL_FULL, lo + bpos, src);
@@ -408,7 +443,7 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC> &sm, co
             const int sym = lo + bpos;
             const int back = act ? sym + pred : 0;
             if (act && sub == 0) {
-                atomicAdd((unsigned *)&hk[(unsigned)sym & 255u] + 1, 1u);   // high word = count
+                atomicAdd((unsigned *)&hk[(unsigned)(sym + rot) & 255u] + 1, 1u);   // high word = count
                 ((unsigned char *)&ws.back[ci][i + 1])[ch] = (unsigned char)back;
             }
             left = back;
@@ -460,18 +495,35 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC> &sm, co
             En0[x] = ws.n0[ci][gl];
             En1[x] = ws.n1[ci][gl];
             rcand[x] = pl_uc4(q4);
-            // derivative error of the three neighbours (reference :265-287)
-            unsigned e = 0;
+            // derivative error of the three neighbours (reference :265-287): for N in {above, diag, left}
+            //   sum over colour lanes of ((oldN - orig) - (newN - back))^2 .
+            // With the four channels of a pixel in one 32-bit word that is a handful of byte dot products
+            // (IDP.4A).  canon() zeroes channels the colour mode does not use and copies G over R and B in
+            // the gray modes, which is how color_difference() counts gray three times (color_delta.c:10-25).
+            {
+                const unsigned o = __byte_perm(o4, 0u, canon), q = __byte_perm(q4, 0u, canon);
+                const unsigned n1o = __byte_perm(oa4, 0u, canon), n1n = __byte_perm(na4, 0u, canon);
+                const unsigned n2o = __byte_perm(oad4, 0u, canon), n2n = __byte_perm(nad4, 0u, canon);
+                const unsigned n3o = __byte_perm(ol4, 0u, canon), n3n = __byte_perm(ql4, 0u, canon);
+                // sum (a - b - c + d)^2 = X - 2Y + 2Z over byte dot products
+                unsigned xs = __dp4a(o, o, __dp4a(q, q, 0u)) * 3u;
+                xs = __dp4a(n1o, n1o, __dp4a(n1n, n1n, xs));
+                xs = __dp4a(n2o, n2o, __dp4a(n2n, n2n, xs));
+                xs = __dp4a(n3o, n3o, __dp4a(n3n, n3n, xs));
+                unsigned ys = __dp4a(o, q, 0u) * 3u;
+                ys = __dp4a(n1o, n1n, __dp4a(n1o, o, __dp4a(n1n, q, ys)));
+                ys = __dp4a(n2o, n2n, __dp4a(n2o, o, __dp4a(n2n, q, ys)));
+                ys = __dp4a(n3o, n3n, __dp4a(n3o, o, __dp4a(n3n, q, ys)));
+                unsigned zs = __dp4a(n1o, q, __dp4a(n1n, o, 0u));
+                zs = __dp4a(n2o, q, __dp4a(n2n, o, zs));
+                zs = __dp4a(n3o, q, __dp4a(n3n, o, zs));
+                derr += xs + 2u * zs - 2u * ys;
+            }
+            if (adaptive) {
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                if ((chmask >> c) & 1) {
-                    const int oc = pl_byte(o4, c), qc = pl_byte(q4, c);
-                    const int da = (pl_byte(oa4, c) - oc) - (pl_byte(na4, c) - qc);
-                    const int dg = (pl_byte(oad4, c) - oc) - (pl_byte(nad4, c) - qc);
-                    const int dl = (pl_byte(ol4, c) - oc) - (pl_byte(ql4, c) - qc);
-                    const unsigned s2 = (unsigned)(da * da + dg * dg + dl * dl);
-                    e += (gray && c == 1) ? 3u * s2 : s2;
-                    if (adaptive) {
+                for (int c = 0; c < 4; c++) {
+                    if ((chmask >> c) & 1) {
+                        const int qc = pl_byte(q4, c);
                         const int lq = pl_byte(ql4, c), aq = pl_byte(na4, c), dq = pl_byte(nad4, c);
                         as0 += pl_absres(qc, 0);
                         as1 += pl_absres(qc, lq);
@@ -481,7 +533,6 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC> &sm, co
                     }
                 }
             }
-            derr += e;
         }
         if (gl == 0 && live) {
             ws.orig[buf ^ 1][ci][0] = ws.orig[buf][ci][npx];
@@ -537,11 +588,12 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC> &sm, co
 }
 
 template <int LPC>
-__global__ void __launch_bounds__(PL_K2_THREADS, PL_K2_MIN_BLOCKS)
+__global__ void __launch_bounds__(PL_K2_THREADS, PL_K2_MIN_BLOCKS(LPC))
 pl_k2_quantize(const PlImageDev *imgs, const int *slots, int strength, int bleed) {
     typedef PlCfg<LPC> C;
     PL_DYN_SMEM(smem_raw);
-    PlCtaSmem<LPC> &sm = *(PlCtaSmem<LPC> *)smem_raw;
+    // 2 KB alignment for the histogram tables (the launch reserves PL_K2_SMEM_ALIGN spare bytes)
+    PlCtaSmem<LPC> &sm = *(PlCtaSmem<LPC> *)pl_align_shared(smem_raw, PL_K2_SMEM_ALIGN);
     const int tid = threadIdx.x;
     const int lane = tid & 31, F = tid >> 5;
     const int ci = lane / C::GROUP, gl = lane % C::GROUP;
@@ -605,8 +657,17 @@ pl_k2_quantize(const PlImageDev *imgs, const int *slots, int strength, int bleed
         int n = 0;
         for (int k = tid; k < C::CPW * PL_FILTERS * 256; k += PL_K2_THREADS, n++) {
             const int c2 = k / (PL_FILTERS * 256), r = k % (PL_FILTERS * 256);
-            sm.hk[c2][r] = (unsigned long long)(my_rank[n] << PL_KEY_RANK_SHIFT);  // count 0
+            my_rank[n] <<= PL_KEY_RANK_SHIFT;
             if (r < 256) sm.base[c2][r] = 0;
+        }
+    }
+    __syncthreads();
+    {
+        int n = 0;
+        for (int k = tid; k < C::CPW * PL_FILTERS * 256; k += PL_K2_THREADS, n++) {
+            const int c2 = k / (PL_FILTERS * 256), r = k % (PL_FILTERS * 256);
+            const int f = r / 256, s = r % 256;
+            sm.hk[c2][f * 256 + ((s + c2 * C::HROT) & 255)] = (unsigned long long)my_rank[n];   // count 0
         }
     }
     __syncthreads();
@@ -703,7 +764,8 @@ pl_k2_quantize(const PlImageDev *imgs, const int *slots, int strength, int bleed
     for (int c2 = 0; c2 < C::CPW; c2++) {
         if (my_slots[c2] < 0) continue;
         const PlImageDev &im = sm.img[c2];
-        for (int s = tid; s < 256; s += PL_K2_THREADS) im.final_hist[s] = sm.base[c2][s];
+        for (int s = tid; s < 256; s += PL_K2_THREADS)
+            im.final_hist[s] = sm.base[c2][(s + c2 * C::HROT) & 255];
     }
     if (valid && F == 0 && gl == 0) {
         const PlImageDev &im = sm.img[ci];

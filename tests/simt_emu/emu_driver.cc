@@ -9,7 +9,7 @@ template <int LPC>
 static void run_k2(const PlImageDev *imgs, const int *slots, int nblocks, int strength, int bleed,
                    int) {
     simt::launch([&] { pl_k2_quantize<LPC>(imgs, slots, strength, bleed); },
-                 dim3(nblocks), dim3(PL_K2_THREADS), sizeof(PlCtaSmem<LPC>));
+                 dim3(nblocks), dim3(PL_K2_THREADS), sizeof(PlCtaSmem<LPC>) + PL_K2_SMEM_ALIGN);
 }
 
 extern "C" int emu_optimize(unsigned char *rgba, int n, uint32_t w, uint32_t h,

@@ -232,6 +232,10 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) {
     }
     return r;
 }
+static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {
+    for (int i = 0; i < 4; i++) c += ((a >> (8 * i)) & 0xffu) * ((b >> (8 * i)) & 0xffu);
+    return c;
+}
 template <class T> static inline T __ldg(const T *p) { return *p; }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
