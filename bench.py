@@ -66,13 +66,19 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """dram bytes per K2 launch from the committed ncu capture, if one exists for this workload."""
+def ncu_traffic(a):
+    """dram bytes per launch from the committed ncu capture (profiles/k2_traffic.json), reported only
+    when that capture was taken on the workload being benchmarked."""
     try:
         with open(os.path.join(ROOT, "profiles", "k2_traffic.json")) as f:
-            return json.load(f)
+            t = json.load(f)
+        w = t["workload"]
+        if (w["images_per_gpu"], w["width"], w["height"], w["strength"]) == (a.images, a.width, a.height,
+                                                                           a.strength):
+            return t
     except Exception:
-        return None
+        pass
+    return None
 
 
 # ---- reference CPU arm ---------------------------------------------------------------------------------
@@ -328,7 +334,7 @@ def main():
         k2_s = float(np.mean(k2_ms)) * 1e-3
         k1_s = float(np.mean(k1_ms)) * 1e-3
         achieved = K2_BYTES_PER_PX * px_per_step_rank / k2_s / 1e9
-        tr = ncu_traffic()
+        tr = ncu_traffic(a)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
