@@ -259,9 +259,15 @@ def main():
     ctx.timer_start()
     t_wall = time.perf_counter()
     for _ in range(a.steps):
+        tw0 = time.perf_counter()
         step()
+        tw1 = time.perf_counter()
         batch.finish()
+        tw2 = time.perf_counter()
         t = batch.timings()
+        if os.environ.get("PNGLOSS_BENCH_TRACE"):
+            print(f"[trace] enqueue {tw1 - tw0:.3f}s finish {tw2 - tw1:.3f}s run_ms {t['run_ms']:.1f}",
+                  file=sys.stderr, flush=True)
         k1_ms.append(t["k1_hist_ms"])
         k2_ms.append(t["k2_quantize_ms"])
         k3_ms.append(t["k3_batch_hist_ms"])

@@ -4,7 +4,7 @@
  * no CUDA or torch types.  It contains no CPU implementation of the path: every entry point runs the
  * sm_100a kernels and fails with PNGLOSS_B200_DEVICE_ERROR when no usable device is present.
  *
- * Part 1 is the drop-in: the three public symbols of the reference's src/pngloss_image.h with the
+ * Part 1 is the drop-in: the four public symbols of the reference's src/pngloss_image.h with the
  * same names, argument meaning, in-place behaviour and error codes, so that the reference's
  * src/pngloss.c:266 call site links against this library unchanged.
  * Part 2 adds what the reference does not have: a batch entry (the reference loops over files one
@@ -50,6 +50,15 @@ void optimize_with_stride(unsigned char *pixels, uint32_t width, uint32_t height
                           int_fast16_t bleed_divider);
 /* replaces reference src/pngloss_image.c:29 (bleed 2, tight stride, row_filters = NULL) */
 void optimizeForAverageFilter(unsigned char pixels[], int width, int height, int quantization);
+/* replaces reference src/pngloss_image.c:159 (declared src/pngloss_image.h:26-29): the inner entry on
+ * a packed image with an explicit bytes_per_pixel of 1 (gray), 2 (gray+alpha), 3 (rgb) or 4 (rgba). */
+typedef struct {
+    unsigned char **rows;
+    uint32_t width, height;
+    uint_fast8_t bytes_per_pixel;
+} pngloss_image;
+int optimize_image(pngloss_image *image, unsigned char *row_filters, bool verbose,
+                   uint_fast8_t quantization_strength, int_fast16_t bleed_divider);
 #endif
 
 /* ------------------------------------------------------------------------------------------------

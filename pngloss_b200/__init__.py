@@ -25,7 +25,7 @@ NO_ACCEPTABLE_ROW = 41
 
 # every symbol include/pngloss_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "optimize_with_rows", "optimize_with_stride", "optimizeForAverageFilter",
+    "optimize_with_rows", "optimize_with_stride", "optimizeForAverageFilter", "optimize_image",
     "pngloss_b200_device_count", "pngloss_b200_ctx_create", "pngloss_b200_ctx_destroy",
     "pngloss_b200_ctx_error", "pngloss_b200_ctx_set_lanes", "pngloss_b200_ctx_timer_start",
     "pngloss_b200_ctx_timer_stop", "pngloss_b200_ctx_sync", "pngloss_b200_host_alloc",
@@ -44,6 +44,12 @@ class PnglossError(RuntimeError):
     def __init__(self, code, msg=""):
         super().__init__(f"pngloss_b200 error {code}: {msg}")
         self.code = code
+
+
+class PnglossImage(ctypes.Structure):
+    """struct pngloss_image (reference src/pngloss_image.h:7-11)."""
+    _fields_ = [("rows", ctypes.POINTER(ctypes.c_void_p)), ("width", ctypes.c_uint32),
+                ("height", ctypes.c_uint32), ("bytes_per_pixel", ctypes.c_uint8)]
 
 
 class ImageDesc(ctypes.Structure):
@@ -72,6 +78,9 @@ def load_library() -> ctypes.CDLL:
     L.optimize_with_rows.restype = i32
     L.optimize_with_stride.argtypes = [vp, u32, u32, u32, ctypes.c_bool, ctypes.c_uint8, ctypes.c_long]
     L.optimize_with_stride.restype = None
+    L.optimize_image.argtypes = [ctypes.POINTER(PnglossImage), vp, ctypes.c_bool, ctypes.c_uint8,
+                                 ctypes.c_long]
+    L.optimize_image.restype = i32
     L.optimizeForAverageFilter.argtypes = [vp, i32, i32, i32]
     L.optimizeForAverageFilter.restype = None
     L.pngloss_b200_device_count.restype = i32
@@ -133,6 +142,19 @@ def optimize_with_rows(rgba: np.ndarray, row_filters: Optional[np.ndarray], verb
     rf = row_filters.ctypes.data if row_filters is not None else None
     return load_library().optimize_with_rows(_row_pointers(rgba), w, h, rf, verbose,
                                              quantization_strength, bleed_divider)
+
+
+def optimize_image(packed: np.ndarray, bytes_per_pixel: int, row_filters: Optional[np.ndarray],
+                   verbose: bool, quantization_strength: int, bleed_divider: int) -> int:
+    """reference src/pngloss_image.c:159 - `packed` (h, w * bytes_per_pixel) uint8, in place."""
+    assert packed.dtype == np.uint8 and packed.ndim == 2 and packed.strides[1] == 1
+    h = packed.shape[0]
+    w = packed.shape[1] // bytes_per_pixel
+    rows = (ctypes.c_void_p * h)(*[packed.ctypes.data + y * packed.strides[0] for y in range(h)])
+    img = PnglossImage(rows, w, h, bytes_per_pixel)
+    rf = row_filters.ctypes.data if row_filters is not None else None
+    return load_library().optimize_image(ctypes.byref(img), rf, verbose, quantization_strength,
+                                         bleed_divider)
 
 
 def optimize_with_stride(rgba: np.ndarray, verbose: bool, quantization_strength: int,

@@ -27,6 +27,7 @@ struct pngloss_b200_ctx {
 
 struct pngloss_b200_batch {
     pngloss_b200_ctx *ctx = nullptr;
+    cudaStream_t stream = nullptr;       // the context's stream
     size_t n = 0;
     std::vector<uint32_t> w, h;
     std::vector<PlImageDev> himgs;
@@ -168,6 +169,7 @@ extern "C" int pngloss_b200_batch_create(pngloss_b200_ctx *ctx, size_t n, const 
     pngloss_b200_batch *b = new (std::nothrow) pngloss_b200_batch();
     if (!b) return PNGLOSS_B200_OUT_OF_MEMORY;
     b->ctx = ctx;
+    b->stream = ctx->stream;
     b->n = n;
     b->w.assign(widths, widths + n);
     b->h.assign(heights, heights + n);
@@ -247,7 +249,7 @@ extern "C" int pngloss_b200_batch_create(pngloss_b200_ctx *ctx, size_t n, const 
 extern "C" void pngloss_b200_batch_destroy(pngloss_b200_batch *b) {
     if (!b) return;
     cudaSetDevice(b->ctx->device);
-    cudaStreamSynchronize(b->ctx->stream);
+    cudaStreamSynchronize(b->stream);
     if (b->ctx->cached == b) b->ctx->cached = nullptr;
     for (int k = 0; k < 4; k++)
         if (b->ev[k]) cudaEventDestroy(b->ev[k]);
@@ -272,7 +274,7 @@ extern "C" int pngloss_b200_batch_upload(pngloss_b200_batch *b, size_t i, const 
     if (stride < rowbytes) return set_err(ctx, PNGLOSS_B200_INVALID_ARGUMENT, "stride < width*4");
     PL_CUDA(ctx, cudaSetDevice(ctx->device));
     PL_CUDA(ctx, cudaMemcpy2DAsync((void *)b->himgs[i].in, rowbytes, pixels, stride, rowbytes, b->h[i],
-                                   cudaMemcpyHostToDevice, ctx->stream));
+                                   cudaMemcpyHostToDevice, b->stream));
     return PNGLOSS_B200_SUCCESS;
 }
 
@@ -300,7 +302,7 @@ extern "C" int pngloss_b200_batch_upload_rows(pngloss_b200_batch *b, size_t i,
     PL_CUDA(ctx, cudaSetDevice(ctx->device));
     for (uint32_t y = 0; y < b->h[i]; y++)
         PL_CUDA(ctx, cudaMemcpyAsync((unsigned char *)b->himgs[i].in + (size_t)y * rowbytes, rows[y],
-                                     rowbytes, cudaMemcpyHostToDevice, ctx->stream));
+                                     rowbytes, cudaMemcpyHostToDevice, b->stream));
     return PNGLOSS_B200_SUCCESS;
 }
 
@@ -310,7 +312,7 @@ extern "C" int pngloss_b200_batch_synth(pngloss_b200_batch *b, size_t i, uint64_
     PL_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t px = (size_t)b->w[i] * b->h[i];
     const unsigned blocks = (unsigned)std::min<size_t>((px + 255) / 256, 148 * 16);
-    pl_k_synth<<<blocks, 256, 0, ctx->stream>>>((uchar4 *)b->himgs[i].in, b->w[i], b->h[i], seed);
+    pl_k_synth<<<blocks, 256, 0, b->stream>>>((uchar4 *)b->himgs[i].in, b->w[i], b->h[i], seed);
     PL_CUDA(ctx, cudaGetLastError());
     return PNGLOSS_B200_SUCCESS;
 }
@@ -325,7 +327,7 @@ static int launch_k2(pngloss_b200_batch *b, int nblocks, unsigned strength, long
                                           (int)smem));
         attr_set[ctx->device & 15] = true;
     }
-    pl_k2_quantize<LPC><<<nblocks, PL_K2_THREADS, smem, ctx->stream>>>(b->dimgs, b->dslots, (int)strength,
+    pl_k2_quantize<LPC><<<nblocks, PL_K2_THREADS, smem, b->stream>>>(b->dimgs, b->dslots, (int)strength,
                                                                       (int)bleed);
     PL_CUDA(ctx, cudaGetLastError());
     b->info[0] = (uint32_t)nblocks;
@@ -334,11 +336,13 @@ static int launch_k2(pngloss_b200_batch *b, int nblocks, unsigned strength, long
     return PNGLOSS_B200_SUCCESS;
 }
 
-// Lane mapping by batch size, from the B200 sweep in profiles/r1_sweep_lanes.txt (3840-wide images):
-// with few images only wide lane groups keep the SMs busy (one image per CTA); from about four images
-// per SM on, packing 4 images per CTA (2 lanes per channel) issues ~3x fewer instructions per pixel.
+// Lane mapping by batch size, from the B200 sweeps in profiles/ (3840-wide images): with few images
+// only wide lane groups keep the SMs busy (one image per CTA); with more images per SM, packing 4 or 8
+// images per CTA issues ~3x fewer instructions per pixel (1184 images: 1.41 Gpx/s at 8 per CTA, 1.27 at
+// 4, 0.86 at 2, 0.55 at 1).
 static int choose_lpc(const pngloss_b200_batch *b) {
     if (b->ctx->lpc) return b->ctx->lpc;
+    if (b->n >= 1184) return 1;
     if (b->n >= 592) return 2;
     if (b->n >= 296) return 4;
     return 8;
@@ -367,22 +371,22 @@ extern "C" int pngloss_b200_batch_run(pngloss_b200_batch *b, unsigned strength, 
     const int nblocks = (int)(b->hslots.size() / cpw);
     if (b->desc_dirty) {
         PL_CUDA(ctx, cudaMemcpyAsync(b->dimgs, b->himgs.data(), b->n * sizeof(PlImageDev),
-                                     cudaMemcpyHostToDevice, ctx->stream));
+                                     cudaMemcpyHostToDevice, b->stream));
         b->desc_dirty = false;
     }
     PL_CUDA(ctx, cudaMemcpyAsync(b->dslots, b->hslots.data(), b->hslots.size() * sizeof(int),
-                                 cudaMemcpyHostToDevice, ctx->stream));
-    PL_CUDA(ctx, cudaMemsetAsync(b->zero_begin, 0, b->zero_bytes, ctx->stream));
+                                 cudaMemcpyHostToDevice, b->stream));
+    PL_CUDA(ctx, cudaMemsetAsync(b->zero_begin, 0, b->zero_bytes, b->stream));
 
     // K1: enough row slices per image to fill the machine, capped by the image height
     uint32_t hmin = b->h[0];
     for (size_t i = 1; i < b->n; i++) hmin = std::min(hmin, b->h[i]);
     size_t want = (4 * 148 + b->n - 1) / b->n;
     unsigned slices = (unsigned)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(want, 256), hmin));
-    PL_CUDA(ctx, cudaEventRecord(b->ev[0], ctx->stream));
-    pl_k1_orig_hist<<<(unsigned)(b->n * slices), PL_K1_THREADS, 0, ctx->stream>>>(b->dimgs, slices);
+    PL_CUDA(ctx, cudaEventRecord(b->ev[0], b->stream));
+    pl_k1_orig_hist<<<(unsigned)(b->n * slices), PL_K1_THREADS, 0, b->stream>>>(b->dimgs, slices);
     PL_CUDA(ctx, cudaGetLastError());
-    PL_CUDA(ctx, cudaEventRecord(b->ev[1], ctx->stream));
+    PL_CUDA(ctx, cudaEventRecord(b->ev[1], b->stream));
     int rc;
     switch (lpc) {
     case 8: rc = launch_k2<8>(b, nblocks, strength, bleed); break;
@@ -391,11 +395,11 @@ extern "C" int pngloss_b200_batch_run(pngloss_b200_batch *b, unsigned strength, 
     default: rc = launch_k2<1>(b, nblocks, strength, bleed); break;
     }
     if (rc) return rc;
-    PL_CUDA(ctx, cudaEventRecord(b->ev[2], ctx->stream));
-    pl_k3_batch_hist<<<(unsigned)std::min<size_t>(b->n, 64), 256, 0, ctx->stream>>>(b->dimgs, (int)b->n,
+    PL_CUDA(ctx, cudaEventRecord(b->ev[2], b->stream));
+    pl_k3_batch_hist<<<(unsigned)std::min<size_t>(b->n, 64), 256, 0, b->stream>>>(b->dimgs, (int)b->n,
                                                                                     b->batch_hist);
     PL_CUDA(ctx, cudaGetLastError());
-    PL_CUDA(ctx, cudaEventRecord(b->ev[3], ctx->stream));
+    PL_CUDA(ctx, cudaEventRecord(b->ev[3], b->stream));
     b->info[3] = 3;
     b->ran = true;
     return PNGLOSS_B200_SUCCESS;
@@ -410,11 +414,11 @@ extern "C" int pngloss_b200_batch_download(pngloss_b200_batch *b, size_t i, unsi
     if (pixels) {
         if (stride < rowbytes) return set_err(ctx, PNGLOSS_B200_INVALID_ARGUMENT, "stride < width*4");
         PL_CUDA(ctx, cudaMemcpy2DAsync(pixels, stride, b->himgs[i].out, rowbytes, rowbytes, b->h[i],
-                                       cudaMemcpyDeviceToHost, ctx->stream));
+                                       cudaMemcpyDeviceToHost, b->stream));
     }
     if (row_filters)
         PL_CUDA(ctx, cudaMemcpyAsync(row_filters, b->himgs[i].filters, b->h[i], cudaMemcpyDeviceToHost,
-                                     ctx->stream));
+                                     b->stream));
     return PNGLOSS_B200_SUCCESS;
 }
 
@@ -429,10 +433,10 @@ extern "C" int pngloss_b200_batch_download_rows(pngloss_b200_batch *b, size_t i,
     PL_CUDA(ctx, cudaSetDevice(ctx->device));
     for (uint32_t y = 0; y < b->h[i]; y++)
         PL_CUDA(ctx, cudaMemcpyAsync(rows[y], (const unsigned char *)b->himgs[i].out + (size_t)y * rowbytes,
-                                     rowbytes, cudaMemcpyDeviceToHost, ctx->stream));
+                                     rowbytes, cudaMemcpyDeviceToHost, b->stream));
     if (row_filters)
         PL_CUDA(ctx, cudaMemcpyAsync(row_filters, b->himgs[i].filters, b->h[i], cudaMemcpyDeviceToHost,
-                                     ctx->stream));
+                                     b->stream));
     return PNGLOSS_B200_SUCCESS;
 }
 
@@ -444,7 +448,7 @@ extern "C" int pngloss_b200_batch_download_input(pngloss_b200_batch *b, size_t i
     if (stride < rowbytes) return set_err(ctx, PNGLOSS_B200_INVALID_ARGUMENT, "stride < width*4");
     PL_CUDA(ctx, cudaSetDevice(ctx->device));
     PL_CUDA(ctx, cudaMemcpy2DAsync(pixels, stride, b->himgs[i].in, rowbytes, rowbytes, b->h[i],
-                                   cudaMemcpyDeviceToHost, ctx->stream));
+                                   cudaMemcpyDeviceToHost, b->stream));
     return PNGLOSS_B200_SUCCESS;
 }
 
@@ -455,8 +459,8 @@ extern "C" int pngloss_b200_batch_finish(pngloss_b200_batch *b, int *status, uin
     PL_CUDA(ctx, cudaSetDevice(ctx->device));
     if (b->ran)
         PL_CUDA(ctx, cudaMemcpyAsync(b->hstatus.data(), b->status, b->n * 4 * sizeof(uint32_t),
-                                     cudaMemcpyDeviceToHost, ctx->stream));
-    PL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                                     cudaMemcpyDeviceToHost, b->stream));
+    PL_CUDA(ctx, cudaStreamSynchronize(b->stream));
     int first = PNGLOSS_B200_SUCCESS;
     for (size_t i = 0; i < b->n; i++) {
         const int st = !b->ran ? PNGLOSS_B200_SUCCESS
@@ -478,8 +482,8 @@ extern "C" int pngloss_b200_batch_image_histogram(pngloss_b200_batch *b, size_t 
     pngloss_b200_ctx *ctx = b->ctx;
     PL_CUDA(ctx, cudaSetDevice(ctx->device));
     PL_CUDA(ctx, cudaMemcpyAsync(out256, b->himgs[i].final_hist, 256 * sizeof(uint32_t),
-                                 cudaMemcpyDeviceToHost, ctx->stream));
-    PL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                                 cudaMemcpyDeviceToHost, b->stream));
+    PL_CUDA(ctx, cudaStreamSynchronize(b->stream));
     return PNGLOSS_B200_SUCCESS;
 }
 
@@ -488,8 +492,8 @@ extern "C" int pngloss_b200_batch_histogram(pngloss_b200_batch *b, uint64_t *out
     pngloss_b200_ctx *ctx = b->ctx;
     PL_CUDA(ctx, cudaSetDevice(ctx->device));
     PL_CUDA(ctx, cudaMemcpyAsync(out256, b->batch_hist, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost,
-                                 ctx->stream));
-    PL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                                 b->stream));
+    PL_CUDA(ctx, cudaStreamSynchronize(b->stream));
     return PNGLOSS_B200_SUCCESS;
 }
 
@@ -525,7 +529,12 @@ extern "C" int pngloss_b200_optimize_batch(pngloss_b200_ctx *ctx, pngloss_b200_i
         w[i] = images[i].width;
         h[i] = images[i].height;
     }
-    // reuse the previous allocation when the shapes repeat (a CLI or service feeding equal batches)
+    // One upload - run - download pass on the context's stream.  Splitting the batch into chunks on
+    // several streams to overlap the PCIe copies with the kernels was measured and rejected: two
+    // co-resident K2 grids do not share the SMs evenly (the older grid's warps win the issue slots, the
+    // younger one finishes 60 % later), which costs more than the ~1.5 s of copies it hides.
+    //
+    // The allocation is reused when the shapes repeat (a CLI or service feeding equal batches).
     pngloss_b200_batch *b = ctx->cached;
     if (b && (b->n != n || b->w != w || b->h != h)) {
         pngloss_b200_batch_destroy(b);
@@ -546,26 +555,28 @@ extern "C" int pngloss_b200_optimize_batch(pngloss_b200_ctx *ctx, pngloss_b200_i
         if (!rc) rc = pngloss_b200_batch_upload(b, i, images[i].pixels, images[i].stride);
     }
     if (!rc) rc = pngloss_b200_batch_run(b, strength, bleed);
-    std::vector<int> st(n);
-    std::vector<uint32_t> bpp(n), retried(n);
+    std::vector<int> st(n, 0);
+    std::vector<uint32_t> bpp(n, 0), retried(n, 0);
     if (!rc) {
         // pixels are only written back for images that succeeded, so a failed image stays untouched
         // like the reference's out-of-memory path (src/pngloss_image.c:98-125)
-        rc = pngloss_b200_batch_finish(b, st.data(), bpp.data(), retried.data());
-        int rc2 = 0;
-        for (size_t i = 0; i < n && !rc2; i++)
+        int frc = pngloss_b200_batch_finish(b, st.data(), bpp.data(), retried.data());
+        if (frc && frc != PNGLOSS_B200_NO_ACCEPTABLE_ROW) rc = frc;
+        for (size_t i = 0; i < n && !rc; i++)
             if (!st[i])
-                rc2 = pngloss_b200_batch_download(b, i, images[i].pixels, images[i].stride,
-                                                  images[i].row_filters);
-        if (!rc2) rc2 = pngloss_b200_ctx_sync(ctx);
-        if (rc2) rc = rc2;
+                rc = pngloss_b200_batch_download(b, i, images[i].pixels, images[i].stride,
+                                                 images[i].row_filters);
+        if (!rc) rc = pngloss_b200_ctx_sync(ctx);
     }
+    int first = rc;
     for (size_t i = 0; i < n; i++) {
-        images[i].status = rc && !st[i] && rc != PNGLOSS_B200_NO_ACCEPTABLE_ROW ? rc : st[i];
+        images[i].status = rc ? rc : st[i];
         images[i].bytes_per_pixel = bpp[i];
         images[i].retried_rows = retried[i];
+        if (!first && st[i]) first = st[i];
     }
-    return rc;
+    if (!rc && first) set_err(ctx, first, "at least one image had no acceptable row even at strength 0");
+    return first;
 }
 
 // ---- drop-in entry points (reference src/pngloss_image.h) ----------------------------------------------
@@ -585,7 +596,8 @@ static pngloss_b200_ctx *default_ctx() {
 }
 
 static int optimize_rows_impl(unsigned char *const *rows, uint32_t width, uint32_t height,
-                              unsigned char *row_filters, bool verbose, unsigned strength, long bleed) {
+                              unsigned char *row_filters, bool verbose, unsigned strength, long bleed,
+                              uint32_t force_bpp = 0) {
     std::lock_guard<std::mutex> lock(g_default_mu);
     pngloss_b200_ctx *ctx = default_ctx();
     if (!ctx) return PNGLOSS_B200_DEVICE_ERROR;
@@ -593,7 +605,7 @@ static int optimize_rows_impl(unsigned char *const *rows, uint32_t width, uint32
     int rc = pngloss_b200_batch_create(ctx, 1, &width, &height, &b);
     if (rc) return rc;
     int st = 0;
-    rc = pngloss_b200_batch_set_mode(b, 0, row_filters == nullptr, 0);
+    rc = pngloss_b200_batch_set_mode(b, 0, row_filters == nullptr, force_bpp);
     if (!rc) rc = pngloss_b200_batch_upload_rows(b, 0, rows);
     if (!rc) rc = pngloss_b200_batch_run(b, strength, bleed);
     if (!rc) rc = pngloss_b200_batch_finish(b, &st, nullptr, nullptr);
@@ -623,6 +635,53 @@ extern "C" int optimize_with_rows(unsigned char **rows, uint32_t width, uint32_t
         // the reference prints and abort()s (src/pngloss_image.c:268-271)
         fprintf(stderr, "\naborting because no good row\n");
         abort();
+    }
+    return rc;
+}
+
+// reference src/pngloss_image.c:159.  The packed 1/2/3-byte pixels are widened to the RGBA layout the
+// kernels work on and narrowed back, the mirror image of what the reference's optimize_with_rows does
+// around this call (src/pngloss_image.c:105-147); the colour mode is forced instead of detected.
+extern "C" int optimize_image(pngloss_image *image, unsigned char *row_filters, bool verbose,
+                              uint_fast8_t quantization_strength, int_fast16_t bleed_divider) {
+    if (!image || !image->rows || image->bytes_per_pixel < 1 || image->bytes_per_pixel > 4)
+        return PNGLOSS_B200_INVALID_ARGUMENT;
+    const uint32_t w = image->width, h = image->height, bpp = image->bytes_per_pixel;
+    if (bpp == 4)
+        return optimize_rows_impl(image->rows, w, h, row_filters, verbose, quantization_strength,
+                                  bleed_divider, 4);
+    std::vector<unsigned char> rgba;
+    std::vector<unsigned char *> rows(h);
+    try {
+        rgba.resize((size_t)w * h * 4);
+    } catch (const std::bad_alloc &) {
+        return PNGLOSS_B200_OUT_OF_MEMORY;
+    }
+    for (uint32_t y = 0; y < h; y++) {
+        rows[y] = rgba.data() + (size_t)y * w * 4;
+        const unsigned char *src = image->rows[y];
+        for (uint32_t x = 0; x < w; x++) {
+            unsigned char *p = rows[y] + (size_t)x * 4;
+            const unsigned char *q = src + (size_t)x * bpp;
+            if (bpp == 3) { p[0] = q[0]; p[1] = q[1]; p[2] = q[2]; p[3] = 255; }
+            else { p[0] = p[1] = p[2] = q[0]; p[3] = bpp == 2 ? q[1] : 255; }
+        }
+    }
+    int rc = optimize_rows_impl(rows.data(), w, h, row_filters, verbose, quantization_strength,
+                                bleed_divider, bpp);
+    if (rc == PNGLOSS_B200_NO_ACCEPTABLE_ROW) {
+        fprintf(stderr, "\naborting because no good row\n");
+        abort();
+    }
+    if (rc) return rc;
+    for (uint32_t y = 0; y < h; y++) {
+        unsigned char *dst = image->rows[y];
+        for (uint32_t x = 0; x < w; x++) {
+            const unsigned char *p = rows[y] + (size_t)x * 4;
+            unsigned char *q = dst + (size_t)x * bpp;
+            if (bpp == 3) { q[0] = p[0]; q[1] = p[1]; q[2] = p[2]; }
+            else { q[0] = p[1]; if (bpp == 2) q[1] = p[3]; }
+        }
     }
     return rc;
 }

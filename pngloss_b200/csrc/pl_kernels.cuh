@@ -143,7 +143,7 @@ struct PlCfg {
     // unroll factor of the candidate scan: ceil((strength + 1) / LPC) candidates per lane, i.e. 3, 6,
     // 11, 21 at the usual strengths 19/20
     static const int UNR = LPC == 8 ? 3 : LPC == 4 ? 3 : 11;
-    static const bool DUAL = LPC <= 2;   // two running maxima in the scan (latency-bound variants)
+    static const int NACC = LPC == 1 ? 4 : LPC == 2 ? 2 : 1;   // running maxima in the scan (measured best)
     static const int LOG2LPC = LPC == 8 ? 3 : LPC == 4 ? 2 : LPC == 2 ? 1 : 0;
     // narrow lane groups scan many candidates per lane: test the one "exact" candidate separately
     // instead of carrying its flag through every candidate
@@ -352,7 +352,11 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC> &sm, co
             // Every lane looks at candidates sub, sub + LPC, ...; the trip count comes from the
             // strength (warp-uniform), candidates beyond the clamped band are predicated off, and the
             // body is unrolled so that the independent shared-memory loads are in flight together.
-            unsigned long long bkey = 0, bkey2 = 0;   // two running maxima: shorter dependency chain
+            // NACC running maxima (merged after the scan) keep the compare chain short where a lane looks
+            // at many candidates
+            unsigned long long acc[C::NACC];
+#pragma unroll
+            for (int k = 0; k < C::NACC; k++) acc[k] = 0;
             {
                 const int jl = (span - sub) >> C::LOG2LPC;          // last valid j of this lane (-1: none)
                 const unsigned off0 = (unsigned)(lo + sub + rot) * 8u;   // byte offset of candidate j = 0
@@ -368,8 +372,8 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC> &sm, co
                         unsigned long long key = pl_hk_load(hkt, off_c + (unsigned)(u * LPC * 8));
                         key |= low_c - (unsigned)(u * LPC);          // low 10 bits of an entry are zero
                         if (!C::EXSEP) key |= (unsigned)(u * LPC == jx_c) << 9;
-                        if (C::DUAL && (u & 1)) bkey2 = (u <= jl_c && key > bkey2) ? key : bkey2;
-                        else bkey = (u <= jl_c && key > bkey) ? key : bkey;
+                        unsigned long long &a = acc[u % C::NACC];
+                        a = (u <= jl_c && key > a) ? key : a;
                     }
                 }
                 if (C::EXSEP) {
@@ -378,10 +382,15 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC> &sm, co
                     const int pos = ex - lo;
                     const unsigned long long key =
                         pl_hk_load(hkt, (unsigned)(ex + rot) * 8u) | pl_key_low(true, pos & 255);
-                    bkey2 = (pos >= 0 && pos <= span && key > bkey2) ? key : bkey2;
+                    unsigned long long &a = acc[C::NACC - 1];
+                    a = (pos >= 0 && pos <= span && key > a) ? key : a;
                 }
-                if (C::DUAL || C::EXSEP) bkey = bkey2 > bkey ? bkey2 : bkey;
             }
+#pragma unroll
+            for (int k = C::NACC / 2; k >= 1; k >>= 1)
+#pragma unroll
+                for (int m = 0; m < k; m++) acc[m] = acc[m + k] > acc[m] ? acc[m + k] : acc[m];
+            unsigned long long bkey = acc[0];
 #pragma unroll
             for (int mk = 1; mk < LPC; mk <<= 1) {
                 const unsigned long long okey = __shfl_xor_sync(PL_FULL, bkey, mk);

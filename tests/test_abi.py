@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_symbols():
     text = open(os.path.join(ROOT, "include", "pngloss_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    names = re.findall(r"\b(pngloss_b200_\w+|optimize_with_rows|optimize_with_stride|"
+    names = re.findall(r"\b(pngloss_b200_\w+|optimize_with_rows|optimize_with_stride|optimize_image|"
                        r"optimizeForAverageFilter)\s*\(", text)
     return sorted(set(names))
 

@@ -1,0 +1,120 @@
+"""GPU tests of the host program (pngloss_b200/host/pngloss): the reference's
+command line surface end to end - PNG in, batched quantise + filter search on the GPU, PNG out - checked
+against the oracle for pixels and per-row filters."""
+import os
+import struct
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from checkers import Oracle
+from golden_cases import GOLDEN, load_input
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "pngloss_b200", "host")
+CLI = os.path.join(HOST, "pngloss")
+MASK_TO_TYPE = {0x08: 0, 0x10: 1, 0x20: 2, 0x40: 3, 0x80: 4}
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _build():
+    subprocess.run(["make", "-s", "-C", HOST], check=True)
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return Oracle()
+
+
+def png_filter_bytes(path):
+    data = open(path, "rb").read()
+    pos, idat, ihdr = 8, b"", None
+    while pos < len(data):
+        n, name = struct.unpack(">I4s", data[pos:pos + 8])
+        if name == b"IHDR":
+            ihdr = data[pos + 8:pos + 8 + n]
+        if name == b"IDAT":
+            idat += data[pos + 8:pos + 8 + n]
+        pos += 12 + n
+    w, h, _, ctype = struct.unpack(">IIBB", ihdr[:10])
+    bpp = {0: 1, 2: 3, 4: 2, 6: 4}[ctype]
+    raw = zlib.decompress(idat)
+    return [raw[y * (1 + w * bpp)] for y in range(h)], ctype
+
+
+def fixture_images(oracle):
+    out = {}
+    for c in GOLDEN:
+        if c["src"]["kind"] == "fixture" and c["src"]["key"] not in out and c["src"]["key"] != "lena":
+            out[c["src"]["key"]] = load_input(c, oracle)
+    return out
+
+
+def test_cli_batch_of_files_matches_oracle(tmp_path, oracle):
+    imgs = fixture_images(oracle)
+    paths = []
+    for key, rgba in imgs.items():
+        p = str(tmp_path / f"{key}.png")
+        Image.fromarray(rgba, "RGBA").save(p)       # every input is an RGBA PNG; the path narrows it itself
+        paths.append(p)
+    r = subprocess.run([CLI, "-v", "-s", "19", "-b", "2", "--", *paths], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert f"Compressed {len(paths)} images." in r.stderr
+    for key, rgba in imgs.items():
+        out = str(tmp_path / f"{key}-loss.png")
+        want_px, want_rf = oracle.optimize(rgba, 19, 2, True)
+        got = np.array(Image.open(out).convert("RGBA"))
+        assert np.array_equal(got, want_px), key
+        filt, ctype = png_filter_bytes(out)
+        assert filt == [MASK_TO_TYPE[m] for m in want_rf], key    # row 0 too: heuristic == chosen filter
+        gray = (want_px[..., 0] == want_px[..., 1]).all() and (want_px[..., 1] == want_px[..., 2]).all()
+        opaque = (want_px[..., 3] == 255).all()
+        assert ctype == {(1, 1): 0, (1, 0): 4, (0, 1): 2, (0, 0): 6}[(int(gray), int(opaque))], key
+        assert os.path.getsize(out) < os.path.getsize(str(tmp_path / f"{key}.png"))
+
+
+def test_cli_stdin_stdout_and_output_options(tmp_path, oracle):
+    rgba = load_input([c for c in GOLDEN if c["name"] == "rose"][0], oracle)
+    src = str(tmp_path / "rose.png")
+    Image.fromarray(rgba, "RGBA").save(src)
+    want_px, _ = oracle.optimize(rgba, 30, 1, True)
+    # the website front end's invocation: pngloss -sN -bN - on stdin/stdout (reference pnglossapi.go:543-556)
+    r = subprocess.run([CLI, "-s30", "-b1", "-"], input=open(src, "rb").read(), capture_output=True)
+    assert r.returncode == 0, r.stderr
+    out = str(tmp_path / "stdout.png")
+    open(out, "wb").write(r.stdout)
+    assert np.array_equal(np.array(Image.open(out).convert("RGBA")), want_px)
+    # -o and --ext
+    dst = str(tmp_path / "explicit.png")
+    assert subprocess.run([CLI, "-s", "30", "-b", "1", "-o", dst, src]).returncode == 0
+    assert np.array_equal(np.array(Image.open(dst).convert("RGBA")), want_px)
+    assert subprocess.run([CLI, "-s", "30", "-b", "1", "--ext", "-q.png", src]).returncode == 0
+    assert np.array_equal(np.array(Image.open(str(tmp_path / "rose-q.png")).convert("RGBA")), want_px)
+    # second run without --force refuses to overwrite, with --force it succeeds
+    assert subprocess.run([CLI, "-s", "30", "-b", "1", "--ext", "-q.png", src],
+                          capture_output=True).returncode == 15
+    assert subprocess.run([CLI, "-f", "-s", "30", "-b", "1", "--ext", "-q.png", src]).returncode == 0
+
+
+def test_cli_skip_if_larger(tmp_path, oracle):
+    """--skip-if-larger: re-compressing the tool's own strength-0 output cannot make it smaller -> exit 98,
+    no output file (reference src/pngloss.c:268-270, rwpng.c:85-105,626-628)."""
+    img = oracle.synth(48, 32, 21)
+    src = str(tmp_path / "in.png")
+    Image.fromarray(img, "RGBA").save(src)
+    first = str(tmp_path / "first.png")
+    assert subprocess.run([CLI, "-s", "0", "-o", first, src]).returncode == 0
+    assert np.array_equal(np.array(Image.open(first).convert("RGBA")), img)        # strength 0 is lossless
+    r = subprocess.run([CLI, "-v", "-s", "0", "--skip-if-larger", first], capture_output=True, text=True)
+    assert r.returncode == 98, r.stderr
+    assert not os.path.exists(str(tmp_path / "first-loss.png"))
+    assert not os.path.exists(str(tmp_path / "first-loss.png.tmp"))
+    assert "Skipped 1 file" in r.stderr
+    # and a clearly compressible case passes the same option
+    assert subprocess.run([CLI, "-s", "40", "--skip-if-larger", src]).returncode == 0
+    assert os.path.getsize(str(tmp_path / "in-loss.png")) < os.path.getsize(src)

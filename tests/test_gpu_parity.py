@@ -158,6 +158,23 @@ def test_secondary_entry_points(oracle):
     assert np.array_equal(tight, want2)
 
 
+def test_optimize_image_packed_entry(oracle):
+    """The reference's inner entry on packed pixels with explicit bytes_per_pixel
+    (src/pngloss_image.c:159), all four modes, against the oracle's restatement of it."""
+    for bpp in (1, 2, 3, 4):
+        rgba = oracle.synth(45, 13, 60 + bpp)
+        chans = {1: [1], 2: [1, 3], 3: [0, 1, 2], 4: [0, 1, 2, 3]}[bpp]
+        packed = np.ascontiguousarray(rgba[:, :, chans]).reshape(13, 45 * bpp)
+        want = packed.copy()
+        want_rf = np.zeros(13, np.uint8)
+        assert oracle.lib.oracle_optimize_image(want.ctypes.data, 45, 13, bpp, 45 * bpp,
+                                                want_rf.ctypes.data, 25, 2, None) == 0
+        got = packed.copy()
+        rf = np.zeros(13, np.uint8)
+        assert pngloss_b200.optimize_image(got, bpp, rf, False, 25, 2) == 0
+        assert np.array_equal(got, want) and np.array_equal(rf, want_rf), bpp
+
+
 def test_non_contiguous_row_pointers(oracle):
     """rows[] need not be equally spaced."""
     import ctypes
@@ -239,6 +256,37 @@ def test_properties_full_size_batch(ctx, oracle):
     assert info["images_per_cta"] == 2 and info["k2_ctas"] == 4
     ctx.set_lanes(0)
     batch.close()
+
+
+def test_large_host_batch_matches_device_resident_path(ctx, oracle):
+    """A few hundred MB through the host-buffer call must equal the device-resident batch path and the
+    golden vector (mixed colour modes inside one batch)."""
+    n, w, h = 160, 1024, 512
+    imgs = [oracle.synth(w, h, 1 + i) for i in range(n)]
+    imgs[5] = to_bpp(imgs[5], 3)
+    imgs[9] = to_bpp(imgs[9], 1)
+    work = [im.copy() for im in imgs]
+    rfs = [np.zeros(h, np.uint8) for _ in range(n)]
+    res = ctx.optimize_batch(work, rfs, 20, 2)
+    assert all(r["status"] == 0 for r in res)
+    assert res[5]["bytes_per_pixel"] == 3 and res[9]["bytes_per_pixel"] == 1
+    golden = [c for c in cases("medium") if c["name"] == "synth1024x512"][0]
+    assert sha16(work[0]) == golden["px_sha"] and sha16(rfs[0]) == golden["filt_sha"]
+    ctx.set_lanes(2)
+    batch = pngloss_b200.Batch(ctx, [w] * n, [h] * n)
+    for i in range(n):
+        batch.upload(i, imgs[i])
+    batch.run(20, 2)
+    st, _, _ = batch.finish()
+    assert (st == 0).all()
+    out = np.zeros((h, w, 4), np.uint8)
+    rf = np.zeros(h, np.uint8)
+    for i in range(n):
+        batch.download(i, out, rf)
+        ctx.sync()
+        assert np.array_equal(out, work[i]) and np.array_equal(rf, rfs[i]), i
+    batch.close()
+    ctx.set_lanes(0)
 
 
 def test_invalid_arguments(ctx):

@@ -83,3 +83,20 @@ def test_trace_cost_identity(oracle):
     assert tr["final_frequency"].sum() == 33 * 12 * 4
     assert (tr["row_costs"].min(axis=1) < np.iinfo(np.uint64).max).all()
     assert (tr["row_strength"] == 20).all()
+
+
+def test_ulog2_identity():
+    """The kernel's bit cost uses 33 + clz32(f) for the reference's ulog2(UINTMAX_MAX / f)
+    (src/optimize_state.c:338,564-572; ulog2 returns the bit length).  Exhaustive near powers of two,
+    random elsewhere."""
+    rng = np.random.default_rng(5)
+    fs = set(int(x) for x in rng.integers(1, 2**31 - 1, 20000))
+    for k in range(31):
+        for d in (-2, -1, 0, 1, 2):
+            f = (1 << k) + d
+            if 1 <= f < 2**31:
+                fs.add(f)
+    fs.update(range(1, 5000))
+    for f in fs:
+        clz32 = 32 - f.bit_length()
+        assert ((2**64 - 1) // f).bit_length() == 33 + clz32, f
