@@ -604,7 +604,10 @@ pl_k2_quantize(const PlImageDev *imgs, const int *slots, int strength, int bleed
     // 2 KB alignment for the histogram tables (the launch reserves PL_K2_SMEM_ALIGN spare bytes)
     PlCtaSmem<LPC> &sm = *(PlCtaSmem<LPC> *)pl_align_shared(smem_raw, PL_K2_SMEM_ALIGN);
     const int tid = threadIdx.x;
-    const int lane = tid & 31, F = tid >> 5;
+    // Warps 0 and 4 of a CTA land on the same SM sub-partition (warp id % 4) and are measurably the
+    // slow pair when few CTAs share an SM (profiles/r1_filter_warp_busy.txt), so they get the two
+    // cheapest predictors (none, up) and Paeth gets a sub-partition of its own.
+    const int lane = tid & 31, F = (0x21340 >> (4 * (tid >> 5))) & 7;   // warp 0..4 -> none, paeth, avg, sub, up
     const int ci = lane / C::GROUP, gl = lane % C::GROUP;
     const int *my_slots = slots + (size_t)blockIdx.x * C::CPW;
 
@@ -683,6 +686,12 @@ pl_k2_quantize(const PlImageDev *imgs, const int *slots, int strength, int bleed
 
     const unsigned bleed_magic = pl_make_magic((unsigned)bleed);
     int prev_w = 0;
+#ifdef PL_K2_PROFILE
+    // debug builds only (tools/sweep.py --profile): cycles each filter warp spends inside the row pass,
+    // returned in place of the first words of final_hist
+    unsigned long long prof_busy = 0;
+    const long long prof_start = clock64();
+#endif
     bool failed = false;       // this chain's image hit "no acceptable row" (reference abort())
     unsigned retries = 0;
 
@@ -693,8 +702,14 @@ pl_k2_quantize(const PlImageDev *imgs, const int *slots, int strength, int bleed
         cn.live = valid && !failed;
         bool pending = cn.live;
         for (;;) {
+#ifdef PL_K2_PROFILE
+            const long long prof_t0 = clock64();
+#endif
             const unsigned long long cost =
                 pl_row_pass<LPC>(sm, cn, F, W, y, y & 1, prev_w, adaptive, bleed_magic);
+#ifdef PL_K2_PROFILE
+            prof_busy += (unsigned long long)(clock64() - prof_t0);
+#endif
             if (gl == 0 && cn.live) sm.cost[ci][F] = cost;
             __syncthreads();
 
@@ -776,6 +791,14 @@ pl_k2_quantize(const PlImageDev *imgs, const int *slots, int strength, int bleed
         for (int s = tid; s < 256; s += PL_K2_THREADS)
             im.final_hist[s] = sm.base[c2][(s + c2 * C::HROT) & 255];
     }
+#ifdef PL_K2_PROFILE
+    __syncthreads();
+    if (lane == 0 && my_slots[0] >= 0) {
+        uint32_t *dbg = sm.img[0].final_hist;
+        dbg[2 * F] = (uint32_t)(prof_busy >> 10);
+        if (F == 0) dbg[10] = (uint32_t)((unsigned long long)(clock64() - prof_start) >> 10);
+    }
+#endif
     if (valid && F == 0 && gl == 0) {
         const PlImageDev &im = sm.img[ci];
         im.status[0] = failed ? PL_ST_NO_ROW : PL_ST_OK;

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--lanes", default="8,4,2,1")
     ap.add_argument("--strength", type=int, default=20)
     ap.add_argument("--reps", type=int, default=1)
+    ap.add_argument("--profile", action="store_true", help="with a -DPL_K2_PROFILE build: per-filter busy cycles")
     a = ap.parse_args()
     ctx = pngloss_b200.Context(0)
     for n in [int(x) for x in a.images.split(",")]:
@@ -35,6 +36,12 @@ def main():
                 t = batch.timings()
                 if best is None or t["k2_quantize_ms"] < best["k2_quantize_ms"]:
                     best = t
+            if a.profile:
+                h0 = batch.image_histogram(0)
+                busy = [int(h0[2 * f]) for f in range(5)]
+                print(json.dumps({"images": n, "lanes": lanes, "busy_kcycles_none_sub_up_avg_paeth": busy,
+                                  "total_kcycles": int(h0[10]),
+                                  "busy_frac": [round(b / max(1, int(h0[10])), 3) for b in busy]}), flush=True)
             px = n * a.width * a.height
             print(json.dumps({"images": n, "w": a.width, "h": a.height, "lanes": lanes,
                               "k1_ms": round(best["k1_hist_ms"], 3), "k2_ms": round(best["k2_quantize_ms"], 3),
