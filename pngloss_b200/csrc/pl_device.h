@@ -17,6 +17,16 @@
 
 #define PL_FULL 0xffffffffu
 
+// Path-coverage counters, only in the emulator build (tests assert that both the fast and the general
+// variants of a code path were exercised); they compile to nothing on the device.
+#ifdef PL_SIMT_EMU
+extern unsigned long long pl_emu_counters[8];
+#define PL_EMU_COUNT(slot) (pl_emu_counters[slot]++)
+#else
+#define PL_EMU_COUNT(slot) ((void)0)
+#endif
+enum { PL_CNT_TAPS_TABLE = 0, PL_CNT_TAPS_COMPUTED = 1, PL_CNT_FIXUP_REPLAY = 2, PL_CNT_FIXUP_SKIPPED = 3 };
+
 // ---- cp.async (LDGSTS): global -> shared without a register round trip ---------------------------
 // 4- and 8-byte forms only exist as .ca; the sources are rows this CTA itself wrote (same SM, so
 // L1 is coherent for them after the CTA barrier) or read-only input.
@@ -63,6 +73,12 @@ __device__ __forceinline__ PlHkTable pl_hk_table(const unsigned long long *tab) 
 __device__ __forceinline__ unsigned long long pl_hk_load(PlHkTable t, unsigned byteoff) {
     return t.p[(byteoff & 0x7f8u) >> 3];
 }
+// caller guarantees byteoff < 2048 (no wrap-around): the address is base + offset, which ptxas folds
+// into the load's immediate field when the offset is base + constant
+__device__ __forceinline__ unsigned long long pl_hk_load_nowrap(PlHkTable t, unsigned byteoff) {
+    if (byteoff >= 2048u) { fprintf(stderr, "simt_emu: histogram table overrun\n"); abort(); }
+    return t.p[byteoff >> 3];
+}
 #else
 struct PlHkTable { unsigned saddr; };
 __device__ __forceinline__ PlHkTable pl_hk_table(const unsigned long long *tab) {
@@ -73,6 +89,11 @@ __device__ __forceinline__ PlHkTable pl_hk_table(const unsigned long long *tab) 
 __device__ __forceinline__ unsigned long long pl_hk_load(PlHkTable t, unsigned byteoff) {
     unsigned long long v;
     asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(t.saddr | (byteoff & 0x7f8u)) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long pl_hk_load_nowrap(PlHkTable t, unsigned byteoff) {
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(t.saddr + byteoff) : "memory");
     return v;
 }
 #endif

@@ -148,6 +148,9 @@ struct PlCfg {
     // narrow lane groups scan many candidates per lane: test the one "exact" candidate separately
     // instead of carrying its flag through every candidate
     static const bool EXSEP = LPC <= 2;
+    // the Sierra tap table pays off where the kernel is instruction bound (wide lane groups, many CTAs per
+    // SM: +8 %); with one or two warps per sub-partition its load latency costs more than it saves (-4 %)
+    static const bool DLUT = LPC >= 4;
     // bank stagger between the histograms of the chains of one warp (64-bit entries, rotation)
     static const int HROT = LPC == 2 ? 8 : LPC == 1 ? 4 : 0;
 };
@@ -168,6 +171,7 @@ struct PlWarpSmem {
 };
 
 #define PL_K2_SMEM_ALIGN 2048
+#define PL_DLUT_HALF 512   /* the Sierra tap table covers error values -512 .. 511 (see pl_pack_taps) */
 
 template <int LPC>
 struct PlCtaSmem {
@@ -177,6 +181,7 @@ struct PlCtaSmem {
     // Chains that share a half-warp usually look at the same symbols (residuals cluster at 0), so the
     // table of chain ci is stored rotated by ci * HROT entries to land in different banks.
     unsigned long long hk[PlCfg<LPC>::CPW][PL_FILTERS * 256];
+    unsigned long long dlut[PlCfg<LPC>::DLUT ? 2 * PL_DLUT_HALF : 1];   // packed Sierra taps by error value
     uint32_t base[PlCfg<LPC>::CPW][256];              // symbol_frequency at the start of the row
     unsigned long long cost[PlCfg<LPC>::CPW][PL_FILTERS];
     PlImageDev img[PlCfg<LPC>::CPW];
@@ -184,6 +189,44 @@ struct PlCtaSmem {
     int retry;
     PlWarpSmem<LPC> w[PL_K2_WARPS];
 };
+
+// The Sierra tap values of one error lane (reference src/optimize_state.c:398-467): d = diff / bleed,
+// then twos = d/16, threes = (d - 4 twos)/8, fours = 2 (d - ...)/9, five = (...)/2 and the remainder, all
+// with C's truncating division.
+struct PlTaps {
+    int twos, threes, fours, five, rem;
+};
+__device__ __forceinline__ PlTaps pl_sierra_taps(int diff, unsigned bleed_magic) {
+    PlTaps t;
+    int dd = pl_sdiv_magic(diff, bleed_magic);
+    t.twos = pl_sdiv_pow2(dd, 4);
+    dd -= 4 * t.twos;
+    t.threes = pl_sdiv_pow2(dd, 3);
+    dd -= 2 * t.threes;
+    t.fours = pl_two_ninths(dd);
+    dd -= 2 * t.fours;
+    t.five = pl_sdiv_pow2(dd, 1);
+    t.rem = dd - t.five;
+    return t;
+}
+// For |diff| < PL_DLUT_HALF all five values fit in signed bytes; K2 keeps them in a per-CTA table
+// indexed by diff (the bleed divider is baked in), which replaces ~20 dependent integer operations
+// per pixel by one shared-memory load.
+__device__ __forceinline__ unsigned long long pl_pack_taps(const PlTaps &t) {
+    return (unsigned long long)(unsigned char)t.twos | ((unsigned long long)(unsigned char)t.threes << 8) |
+           ((unsigned long long)(unsigned char)t.fours << 16) | ((unsigned long long)(unsigned char)t.five << 24) |
+           ((unsigned long long)(unsigned char)t.rem << 32);
+}
+__device__ __forceinline__ PlTaps pl_unpack_taps(unsigned long long e) {
+    PlTaps t;
+    const unsigned lo = (unsigned)e;
+    t.twos = (int)(signed char)lo;
+    t.threes = (int)(signed char)(lo >> 8);
+    t.fours = (int)(signed char)(lo >> 16);
+    t.five = (int)(signed char)(lo >> 24);
+    t.rem = (int)(signed char)(unsigned)(e >> 32);
+    return t;
+}
 
 // colour mode of an image: forced, or detected by K1's scan (reference src/pngloss_image.c:64-93)
 __device__ __forceinline__ int pl_image_mode(const PlImageDev &im) {
@@ -423,7 +466,10 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC> &sm, co
                                 (pos != bpos) & ((theirs >> 8) + 3u >= bf);
                 }
             }
-            if (__any_sync(PL_FULL, conflict)) {
+            if (!__any_sync(PL_FULL, conflict)) {
+                PL_EMU_COUNT(PL_CNT_FIXUP_SKIPPED);
+            } else {
+                PL_EMU_COUNT(PL_CNT_FIXUP_REPLAY);
                 // Slow path (rare once counts have spread): the exact sequential replay.
 #pragma unroll 1
                 for (int t2 = 0; t2 < 3; t2++) {
@@ -459,16 +505,16 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC> &sm, co
             aprev = a;
 
             // ---- Sierra diffusion of (here - back) / bleed (reference :390-467) ------------------
-            int dd = act ? pl_sext16(here - back) : 0;
-            dd = pl_sdiv_magic(dd, bleed_magic);
-            const int twos = pl_sdiv_pow2(dd, 4);
-            dd -= 4 * twos;
-            const int threes = pl_sdiv_pow2(dd, 3);
-            dd -= 2 * threes;
-            const int fours = pl_two_ninths(dd);
-            dd -= 2 * fours;
-            const int five = pl_sdiv_pow2(dd, 1);
-            dd -= five;
+            const int diff = act ? pl_sext16(here - back) : 0;
+            PlTaps tp;
+            if (C::DLUT && __all_sync(PL_FULL, (unsigned)(diff + PL_DLUT_HALF) < 2u * PL_DLUT_HALF)) {
+                PL_EMU_COUNT(PL_CNT_TAPS_TABLE);
+                tp = pl_unpack_taps(sm.dlut[diff + PL_DLUT_HALF]);
+            } else {
+                PL_EMU_COUNT(PL_CNT_TAPS_COMPUTED);
+                tp = pl_sierra_taps(diff, bleed_magic);
+            }
+            const int twos = tp.twos, threes = tp.threes, fours = tp.fours, five = tp.five, dd = tp.rem;
             a1 += dd;
             a2 += threes;
             b0 += twos;
@@ -685,6 +731,10 @@ pl_k2_quantize(const PlImageDev *imgs, const int *slots, int strength, int bleed
     __syncthreads();
 
     const unsigned bleed_magic = pl_make_magic((unsigned)bleed);
+    if (C::DLUT)
+        for (int k = tid; k < 2 * PL_DLUT_HALF; k += PL_K2_THREADS)
+            sm.dlut[k] = pl_pack_taps(pl_sierra_taps(k - PL_DLUT_HALF, bleed_magic));
+    __syncthreads();
     int prev_w = 0;
 #ifdef PL_K2_PROFILE
     // debug builds only (tools/sweep.py --profile): cycles each filter warp spends inside the row pass,

@@ -40,6 +40,12 @@ class Emu:
         return dict(pixels=buf, filters=filt, final_hist=final, status=status, batch_hist=batch,
                     chan_hist=chan)
 
+    def counters(self):
+        """Sierra taps from the table / computed, channel fix-up replays / skips executed so far (per lane)."""
+        out = (ctypes.c_ulonglong * 8)()
+        self.lib.emu_counters(out)
+        return dict(taps_table=out[0], taps_computed=out[1], fixup_replay=out[2], fixup_skipped=out[3])
+
     def synth(self, w, h, seed):
         a = np.zeros((h, w, 4), np.uint8)
         self.lib.emu_synth(a.ctypes.data, w, h, seed)

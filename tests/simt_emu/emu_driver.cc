@@ -71,3 +71,6 @@ extern "C" void emu_synth(unsigned char *dst, uint32_t w, uint32_t h, unsigned l
 }
 
 extern "C" unsigned long long emu_collectives() { return simt::n_collectives; }
+
+unsigned long long pl_emu_counters[8] = {0};
+extern "C" void emu_counters(unsigned long long *out) { memcpy(out, pl_emu_counters, sizeof pl_emu_counters); }

@@ -100,6 +100,21 @@ def test_emu_noise_and_ties(emu, oracle):
         compare(emu, oracle, [few, noise, holes, to_bpp(holes, 2)], 200, 1, True, lpc)
 
 
+def test_emu_both_variants_of_each_path_ran(emu, oracle):
+    """The kernel has a table and a computed variant of the Sierra taps and a skipped and a replayed
+    variant of the channel fix-up; all four must have run (and stayed bit-exact)."""
+    before = emu.counters()
+    smooth = oracle.synth(40, 24, 5)
+    compare(emu, oracle, [smooth], 20, 2, False, 8)          # lanes 8: taps from the table
+    compare(emu, oracle, [smooth, smooth], 20, 2, False, 1)  # lanes 1: taps computed
+    rng = np.random.default_rng(3)
+    noisy = rng.integers(0, 256, (8, 24, 4), dtype=np.uint8)
+    compare(emu, oracle, [noisy], 255, 1, False, 8)          # errors beyond the table range
+    after = emu.counters()
+    for key in ("taps_table", "taps_computed", "fixup_replay", "fixup_skipped"):
+        assert after[key] > before[key], key
+
+
 def test_emu_k1_histograms(emu, oracle):
     """K1's per-channel histograms, folded by colour mode, equal optimize_state_init's table."""
     for bpp in (1, 2, 3, 4):
