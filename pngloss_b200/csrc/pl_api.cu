@@ -519,13 +519,21 @@ extern "C" int pngloss_b200_batch_launch_info(pngloss_b200_batch *b, uint32_t in
     return PNGLOSS_B200_SUCCESS;
 }
 
+// Upper bound of what pngloss_b200_batch_create allocates for one image (see its slab layout).
+static size_t device_bytes_per_image(uint32_t w, uint32_t h) {
+    const size_t px = (size_t)w * h;
+    return 2 * align_up(px * 4, 256) + align_up(h, 16) +
+           align_up((size_t)2 * PL_FILTERS * 2 * (w + PL_ERR_PAD) * sizeof(short4), 256) +
+           align_up((size_t)PL_FILTERS * w * 4, 256) + PL_FILTERS * 4 * 256 * sizeof(uint32_t) +
+           256 * sizeof(uint32_t) + sizeof(PlImageDev) + 8 * sizeof(int) + 64 + 1024;
+}
+
 // ---- host-buffer batch ---------------------------------------------------------------------------------
-extern "C" int pngloss_b200_optimize_batch(pngloss_b200_ctx *ctx, pngloss_b200_image *images, size_t n,
-                                           unsigned strength, long bleed) {
-    if (!ctx || !images || !n) return PNGLOSS_B200_INVALID_ARGUMENT;
+// One group of images that fits the device: upload, run, download on the context's stream.
+static int optimize_group(pngloss_b200_ctx *ctx, pngloss_b200_image *images, size_t n, unsigned strength,
+                          long bleed) {
     std::vector<uint32_t> w(n), h(n);
     for (size_t i = 0; i < n; i++) {
-        if (!images[i].pixels) return set_err(ctx, PNGLOSS_B200_INVALID_ARGUMENT, "image %zu: NULL pixels", i);
         w[i] = images[i].width;
         h[i] = images[i].height;
     }
@@ -576,6 +584,35 @@ extern "C" int pngloss_b200_optimize_batch(pngloss_b200_ctx *ctx, pngloss_b200_i
         if (!first && st[i]) first = st[i];
     }
     if (!rc && first) set_err(ctx, first, "at least one image had no acceptable row even at strength 0");
+    return first;
+}
+
+extern "C" int pngloss_b200_optimize_batch(pngloss_b200_ctx *ctx, pngloss_b200_image *images, size_t n,
+                                           unsigned strength, long bleed) {
+    if (!ctx || !images || !n) return PNGLOSS_B200_INVALID_ARGUMENT;
+    for (size_t i = 0; i < n; i++)
+        if (!images[i].pixels) return set_err(ctx, PNGLOSS_B200_INVALID_ARGUMENT, "image %zu: NULL pixels", i);
+    PL_CUDA(ctx, cudaSetDevice(ctx->device));
+    // A batch larger than the free device memory is processed as consecutive groups that fit (the
+    // reference has no such limit: it holds one image at a time, src/pngloss.c:173-205).
+    size_t free_b = 0, total_b = 0;
+    PL_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = (size_t)(0.92 * (double)(free_b + (ctx->cached ? ctx->cached->slab_bytes : 0)));
+    if (const char *e = getenv("PNGLOSS_B200_MEM_BUDGET_MB"))   // tests: force the grouping on small inputs
+        budget = std::min(budget, (size_t)strtoull(e, nullptr, 10) << 20);
+    int first = 0;
+    for (size_t begin = 0; begin < n;) {
+        size_t end = begin, need = 0;
+        while (end < n) {
+            const size_t one = device_bytes_per_image(images[end].width, images[end].height);
+            if (end > begin && need + one > budget) break;
+            need += one;
+            end++;
+        }
+        const int rc = optimize_group(ctx, images + begin, end - begin, strength, bleed);
+        if (rc && !first) first = rc;
+        begin = end;
+    }
     return first;
 }
 

@@ -8,6 +8,8 @@
  * one pngloss_b200_optimize_batch() call and then encodes.  Per-file results are identical.
  */
 #include <getopt.h>
+#include <pthread.h>
+#include <stdatomic.h>
 #include <stdbool.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -31,6 +33,8 @@ options:\n\
   --skip-if-larger  only save converted files if they're smaller than original\n\
   --ext new.png     set custom suffix/extension for output filenames\n\
   --strip           remove optional metadata\n\
+  --gpus N          shard the files over N GPUs (default 1, 0 = all visible) [new]\n\
+  --jobs N          CPU threads for PNG decoding / encoding (default: all cores) [new]\n\
 \n\
 Lossily compresses PNGs by using more compressible colors that are close\n\
 enough to the original color values (strength sets what is close enough).\n\
@@ -47,11 +51,12 @@ struct options {
     char *const *files;
     unsigned long strength, bleed_divider;
     unsigned int num_files;
+    unsigned long gpus, cpu_jobs;   /* additions of this build; everything else is the reference's */
     bool using_stdin, using_stdout, force, skip_if_larger, strip, print_help, print_version, missing_arguments,
         verbose;
 };
 
-enum { arg_ext = 1000, arg_no_force, arg_skip_larger, arg_strip };
+enum { arg_ext = 1000, arg_no_force, arg_skip_larger, arg_strip, arg_gpus, arg_jobs };
 
 static const struct option long_options[] = {
     {"verbose", no_argument, NULL, 'v'},       {"quiet", no_argument, NULL, 'q'},
@@ -60,6 +65,7 @@ static const struct option long_options[] = {
     {"output", required_argument, NULL, 'o'},  {"strip", no_argument, NULL, arg_strip},
     {"version", no_argument, NULL, 'V'},       {"help", no_argument, NULL, 'h'},
     {"strength", required_argument, NULL, 's'}, {"bleed", required_argument, NULL, 'b'},
+    {"gpus", required_argument, NULL, arg_gpus}, {"jobs", required_argument, NULL, arg_jobs},
     {NULL, 0, NULL, 0},
 };
 
@@ -102,6 +108,18 @@ static pngloss_error parse_options(int argc, char *argv[], struct options *o) {
         case 'b':
             if (!parse_number(optarg, &o->bleed_divider)) {
                 fputs("-b, --bleed requires a numeric argument\n", stderr);
+                return INVALID_ARGUMENT;
+            }
+            break;
+        case arg_gpus:
+            if (!parse_number(optarg, &o->gpus)) {
+                fputs("--gpus requires a numeric argument\n", stderr);
+                return INVALID_ARGUMENT;
+            }
+            break;
+        case arg_jobs:
+            if (!parse_number(optarg, &o->cpu_jobs) || !o->cpu_jobs) {
+                fputs("--jobs requires a positive numeric argument\n", stderr);
                 return INVALID_ARGUMENT;
             }
             break;
@@ -162,17 +180,27 @@ struct job {
     unsigned char *row_filters;
     pngloss_error rc;
     bool loaded;
+    char *log;          /* this file's messages, printed in file order once a phase is over */
+    size_t log_len;
+    FILE *logf;
 };
 
-static pngloss_error read_image(const char *filename, bool using_stdin, png24_image *img, bool strip, bool verbose) {
+struct run {
+    const struct options *o;
+    struct job *jobs;
+    unsigned n;
+};
+
+static pngloss_error read_image(const char *filename, bool using_stdin, png24_image *img, bool strip, bool verbose,
+                                FILE *log) {
     FILE *in = using_stdin ? stdin : fopen(filename, "rb");
     if (!in) {
-        fprintf(stderr, "  error: cannot open %s for reading\n", filename);
+        fprintf(log, "  error: cannot open %s for reading\n", filename);
         return READ_ERROR;
     }
     pngloss_error rc = rwpng_read_image24(in, img, strip, verbose);
     if (!using_stdin) fclose(in);
-    if (rc) fprintf(stderr, "  error: cannot decode image %s\n", using_stdin ? "from stdin" : filename_part(filename));
+    if (rc) fprintf(log, "  error: cannot decode image %s\n", using_stdin ? "from stdin" : filename_part(filename));
     return rc;
 }
 
@@ -195,22 +223,22 @@ static pngloss_error prepare_output_image(const png24_image *in, png24_image *ou
 
 /* reference src/pngloss.c:375-431: temp file + rename so that a failed write never damages the target */
 static pngloss_error write_image(png24_image *img, unsigned char *row_filters, const char *outname,
-                                 const struct options *o) {
+                                 const struct options *o, FILE *log) {
     FILE *out;
     char *tempname = NULL;
     if (o->using_stdout) {
         out = stdout;
-        if (o->verbose) fprintf(stderr, "  writing compressed image to stdout\n");
+        if (o->verbose) fprintf(log, "  writing compressed image to stdout\n");
     } else {
         tempname = malloc(strlen(outname) + 5);
         if (!tempname) return OUT_OF_MEMORY_ERROR;
         sprintf(tempname, "%s.tmp", outname);
         if (!(out = fopen(tempname, "wb"))) {
-            fprintf(stderr, "  error: cannot open '%s' for writing\n", tempname);
+            fprintf(log, "  error: cannot open '%s' for writing\n", tempname);
             free(tempname);
             return CANT_WRITE_ERROR;
         }
-        if (o->verbose) fprintf(stderr, "  writing compressed image as %s\n", filename_part(outname));
+        if (o->verbose) fprintf(log, "  writing compressed image as %s\n", filename_part(outname));
     }
     pngloss_error rc = rwpng_write_image24(out, img, row_filters);
     if (!o->using_stdout) {
@@ -222,8 +250,228 @@ static pngloss_error write_image(png24_image *img, unsigned char *row_filters, c
     }
     free(tempname);
     if (rc && rc != TOO_LARGE_FILE)
-        fprintf(stderr, "  error: failed writing image to %s (%d)\n", o->using_stdout ? "stdout" : outname, rc);
+        fprintf(log, "  error: failed writing image to %s (%d)\n", o->using_stdout ? "stdout" : outname, rc);
     return rc;
+}
+
+/* ---- a small parallel-for over the files (decode and encode are independent per file) ------------------- */
+struct pfor {
+    void (*fn)(struct run *, unsigned);
+    struct run *r;
+    atomic_uint next;
+};
+
+static void *pfor_worker(void *arg) {
+    struct pfor *p = arg;
+    for (;;) {
+        unsigned i = atomic_fetch_add(&p->next, 1);
+        if (i >= p->r->n) break;
+        p->fn(p->r, i);
+    }
+    return NULL;
+}
+
+static void parallel_for(struct run *r, void (*fn)(struct run *, unsigned)) {
+    unsigned threads = (unsigned)r->o->cpu_jobs;
+    if (!threads) {
+        long cores = sysconf(_SC_NPROCESSORS_ONLN);
+        threads = cores > 0 ? (unsigned)cores : 1;
+    }
+    if (threads > r->n) threads = r->n;
+    struct pfor p = {fn, r, 0};
+    if (threads <= 1 || r->o->using_stdin) {
+        pfor_worker(&p);
+        return;
+    }
+    pthread_t *tid = calloc(threads, sizeof *tid);
+    unsigned started = 0;
+    for (; tid && started < threads; started++)
+        if (pthread_create(&tid[started], NULL, pfor_worker, &p)) break;
+    if (!started) pfor_worker(&p);
+    for (unsigned k = 0; k < started; k++) pthread_join(tid[k], NULL);
+    free(tid);
+}
+
+static void flush_logs(struct run *r) {
+    for (unsigned i = 0; i < r->n; i++) {
+        struct job *j = &r->jobs[i];
+        if (j->logf) {
+            fclose(j->logf);
+            j->logf = NULL;
+        }
+        if (j->log && j->log_len) fwrite(j->log, 1, j->log_len, stderr);
+        free(j->log);
+        j->log = NULL;
+        j->log_len = 0;
+        j->logf = open_memstream(&j->log, &j->log_len);
+        if (!j->logf) j->logf = stderr;
+    }
+}
+
+/* phase 1 for one file: name, overwrite check, decode (reference src/pngloss.c:173-259) */
+static void decode_job(struct run *r, unsigned i) {
+    const struct options *o = r->o;
+    struct job *j = &r->jobs[i];
+    j->filename = o->using_stdin ? "stdin" : o->files[i];
+    j->outname = (char *)o->output_file_path;
+    if (!o->using_stdout) {
+        if (!j->outname) j->outname = j->outname_free = add_filename_extension(j->filename, o->extension);
+        if (!o->force && file_exists(j->outname)) {
+            fprintf(j->logf, "  error: '%s' exists; not overwriting\n", j->outname);
+            j->rc = NOT_OVERWRITING_ERROR;
+            return;
+        }
+    }
+    if (o->verbose) fprintf(j->logf, "%s:\n", j->filename);
+    j->rc = read_image(j->filename, o->using_stdin, &j->input, o->strip, o->verbose, j->logf);
+    if (j->rc) return;
+    if (o->verbose) {
+        fprintf(j->logf, "  read %luKB file\n", (unsigned long)(j->input.file_size + 500UL) / 1000UL);
+        if (j->input.input_color == RWPNG_SRGB) fprintf(j->logf, "  passing sRGB tag from the input\n");
+        else if (j->input.gamma != 0.45455)
+            fprintf(j->logf, "  converted image from gamma %2.1f to gamma 2.2\n", 1.0 / j->input.gamma);
+    }
+    j->rc = prepare_output_image(&j->input, &j->output);
+    j->row_filters = malloc(j->input.height);   /* NULL is a valid value (reference :262-263) */
+    if (!j->rc) j->loaded = true;
+}
+
+/* phase 3 for one file: encode (reference src/pngloss.c:268-300) */
+static void encode_job(struct run *r, unsigned i) {
+    const struct options *o = r->o;
+    struct job *j = &r->jobs[i];
+    if (!j->loaded || j->rc != SUCCESS) return;
+    if (o->skip_if_larger) j->output.maximum_file_size = j->input.file_size - 1;
+    j->output.chunks = j->input.chunks;
+    j->input.chunks = NULL;
+    j->rc = write_image(&j->output, j->row_filters, j->outname, o, j->logf);
+    if (o->verbose) {
+        if (j->rc == SUCCESS) {
+            fprintf(j->logf, "  wrote %luKB file (%.1f%% of original)\n",
+                    ((unsigned long)j->output.file_size + 500UL) / 1000UL,
+                    100.0f * (float)j->output.file_size / (float)j->input.file_size);
+            if (j->output.metadata_size > 0)
+                fprintf(j->logf, "  copied %dKB of additional PNG metadata\n",
+                        (int)(j->output.metadata_size + 500) / 1000);
+        } else if (j->rc == TOO_LARGE_FILE) {
+            fprintf(j->logf, "  file exceeded maximum size of %luKB\n",
+                    ((unsigned long)j->output.maximum_file_size + 500UL) / 1000UL);
+        }
+    }
+    /* on stdout an empty result would be nasty: send the original instead (reference :286-293) */
+    if (o->using_stdout && j->rc == TOO_LARGE_FILE) {
+        pngloss_error wrc = write_image(&j->input, NULL, j->outname, o, j->logf);
+        if (wrc) j->rc = wrc;
+    }
+}
+
+/* ---- phase 2: the GPU(s).  One host thread and one context per GPU, images assigned longest first ------ */
+struct gpu_shard {
+    int device;
+    pngloss_b200_image *images;
+    unsigned *job_index;
+    unsigned n;
+    unsigned long long pixels;
+    unsigned strength;
+    long bleed;
+    int rc;
+    char err[256];
+};
+
+static void *gpu_worker(void *arg) {
+    struct gpu_shard *s = arg;
+    pngloss_b200_ctx *ctx = NULL;
+    s->rc = pngloss_b200_ctx_create(&ctx, s->device, NULL);
+    if (s->rc) {
+        snprintf(s->err, sizeof s->err, "no usable CUDA device %d (pngloss_b200 has no CPU fallback)", s->device);
+        return NULL;
+    }
+    s->rc = pngloss_b200_optimize_batch(ctx, s->images, s->n, s->strength, s->bleed);
+    if (s->rc && s->rc != PNGLOSS_B200_NO_ACCEPTABLE_ROW) snprintf(s->err, sizeof s->err, "%s", pngloss_b200_ctx_error(ctx));
+    pngloss_b200_ctx_destroy(ctx);
+    return NULL;
+}
+
+static int by_pixels_desc(const void *a, const void *b) {
+    const pngloss_b200_image *x = a, *y = b;
+    const unsigned long long px = (unsigned long long)x->width * x->height, py = (unsigned long long)y->width * y->height;
+    return px < py ? 1 : px > py ? -1 : 0;
+}
+
+static void run_gpus(struct run *r) {
+    const struct options *o = r->o;
+    unsigned n_loaded = 0;
+    for (unsigned i = 0; i < r->n; i++) n_loaded += r->jobs[i].loaded;
+    if (!n_loaded) return;
+    int visible = pngloss_b200_device_count();
+    int first_dev = getenv("PNGLOSS_B200_DEVICE") ? atoi(getenv("PNGLOSS_B200_DEVICE")) : 0;
+    unsigned ngpu = o->gpus ? (unsigned)o->gpus : (visible > 0 ? (unsigned)visible : 1);
+    if (visible > 0 && ngpu > (unsigned)visible) ngpu = (unsigned)visible;
+    if (ngpu > n_loaded) ngpu = n_loaded;
+    if (!ngpu) ngpu = 1;
+
+    /* all loaded images, largest first, each to the GPU with the fewest pixels so far */
+    struct tagged { pngloss_b200_image im; unsigned job; } *all = calloc(n_loaded, sizeof *all);
+    struct gpu_shard *shards = calloc(ngpu, sizeof *shards);
+    unsigned k = 0;
+    for (unsigned i = 0; i < r->n; i++) {
+        struct job *j = &r->jobs[i];
+        if (!j->loaded) continue;
+        all[k].im.pixels = j->output.rgba_data;
+        all[k].im.stride = (size_t)j->output.width * 4;
+        all[k].im.width = j->output.width;
+        all[k].im.height = j->output.height;
+        all[k].im.row_filters = j->row_filters;
+        all[k].job = i;
+        k++;
+    }
+    qsort(all, n_loaded, sizeof *all, by_pixels_desc);   /* struct starts with the image: same comparator */
+    for (unsigned g = 0; g < ngpu; g++) {
+        shards[g].device = first_dev + (int)g;
+        shards[g].images = calloc(n_loaded, sizeof(pngloss_b200_image));
+        shards[g].job_index = calloc(n_loaded, sizeof(unsigned));
+        shards[g].strength = (unsigned)o->strength;
+        shards[g].bleed = (long)o->bleed_divider;
+    }
+    for (unsigned i = 0; i < n_loaded; i++) {
+        unsigned best = 0;
+        for (unsigned g = 1; g < ngpu; g++)
+            if (shards[g].pixels < shards[best].pixels) best = g;
+        struct gpu_shard *s = &shards[best];
+        s->images[s->n] = all[i].im;
+        s->job_index[s->n++] = all[i].job;
+        s->pixels += (unsigned long long)all[i].im.width * all[i].im.height;
+    }
+    pthread_t *tid = calloc(ngpu, sizeof *tid);
+    for (unsigned g = 0; g < ngpu; g++)
+        if (ngpu == 1 || pthread_create(&tid[g], NULL, gpu_worker, &shards[g])) {
+            gpu_worker(&shards[g]);
+            tid[g] = 0;
+        }
+    for (unsigned g = 0; g < ngpu; g++)
+        if (ngpu > 1 && tid[g]) pthread_join(tid[g], NULL);
+
+    for (unsigned g = 0; g < ngpu; g++) {
+        struct gpu_shard *s = &shards[g];
+        if (s->rc && s->err[0]) fprintf(stderr, "  error: %s\n", s->err);
+        for (unsigned q = 0; q < s->n; q++) {
+            struct job *j = &r->jobs[s->job_index[q]];
+            const int st = s->rc && !s->images[q].status ? s->rc : s->images[q].status;
+            if (st == PNGLOSS_B200_NO_ACCEPTABLE_ROW) {
+                fprintf(stderr, "\naborting because no good row in %s\n", j->filename);   /* reference abort()s */
+                abort();
+            }
+            if (st) j->rc = st == PNGLOSS_B200_OUT_OF_MEMORY ? OUT_OF_MEMORY_ERROR : PNGLOSS_DEVICE_ERROR;
+            else if (o->verbose)
+                fprintf(j->logf, "%s:\n  compression complete (%u bytes per pixel, GPU %d)\n", j->filename,
+                        s->images[q].bytes_per_pixel, s->device);
+        }
+        free(s->images);
+        free(s->job_index);
+    }
+    free(tid);
+    free(shards);
+    free(all);
 }
 
 int main(int argc, char *argv[]) {
@@ -231,6 +479,7 @@ int main(int argc, char *argv[]) {
     memset(&o, 0, sizeof o);
     o.strength = 19;
     o.bleed_divider = 2;
+    o.gpus = 1;
     pngloss_error rc = parse_options(argc, argv, &o);
     if (rc != SUCCESS) return rc;
 
@@ -264,104 +513,22 @@ int main(int argc, char *argv[]) {
         return MISSING_ARGUMENT;
     }
 
-    const unsigned n = o.num_files;
-    struct job *jobs = calloc(n, sizeof *jobs);
-    pngloss_b200_image *gpu_jobs = calloc(n, sizeof *gpu_jobs);
-    unsigned *gpu_index = calloc(n, sizeof *gpu_index);
-    if (!jobs || !gpu_jobs || !gpu_index) return OUT_OF_MEMORY_ERROR;
+    struct run r = {&o, calloc(o.num_files, sizeof(struct job)), o.num_files};
+    if (!r.jobs) return OUT_OF_MEMORY_ERROR;
+    flush_logs(&r);                    /* opens the per-file message buffers */
 
-    /* ---- 1. names, overwrite check, decode (reference src/pngloss.c:173-259, per file) ---------------- */
-    unsigned n_gpu = 0;
-    for (unsigned i = 0; i < n; i++) {
-        struct job *j = &jobs[i];
-        j->filename = o.using_stdin ? "stdin" : o.files[i];
-        j->outname = (char *)o.output_file_path;
-        if (!o.using_stdout) {
-            if (!j->outname) j->outname = j->outname_free = add_filename_extension(j->filename, o.extension);
-            if (!o.force && file_exists(j->outname)) {
-                fprintf(stderr, "  error: '%s' exists; not overwriting\n", j->outname);
-                j->rc = NOT_OVERWRITING_ERROR;
-                continue;
-            }
-        }
-        if (o.verbose) fprintf(stderr, "%s:\n", j->filename);
-        j->rc = read_image(j->filename, o.using_stdin, &j->input, o.strip, o.verbose);
-        if (j->rc) continue;
-        if (o.verbose) {
-            fprintf(stderr, "  read %luKB file\n", (unsigned long)(j->input.file_size + 500UL) / 1000UL);
-            if (j->input.input_color == RWPNG_SRGB) fprintf(stderr, "  passing sRGB tag from the input\n");
-            else if (j->input.gamma != 0.45455)
-                fprintf(stderr, "  converted image from gamma %2.1f to gamma 2.2\n", 1.0 / j->input.gamma);
-        }
-        j->rc = prepare_output_image(&j->input, &j->output);
-        j->row_filters = malloc(j->input.height);   /* NULL is a valid value (reference :262-263) */
-        if (j->rc) continue;
-        j->loaded = true;
-        pngloss_b200_image *g = &gpu_jobs[n_gpu];
-        g->pixels = j->output.rgba_data;
-        g->stride = (size_t)j->output.width * 4;
-        g->width = j->output.width;
-        g->height = j->output.height;
-        g->row_filters = j->row_filters;
-        gpu_index[n_gpu++] = i;
-    }
+    parallel_for(&r, decode_job);      /* 1. decode every input (CPU threads) */
+    flush_logs(&r);
+    run_gpus(&r);                      /* 2. one batched call per GPU replaces the per-file optimize_with_rows
+                                             (reference src/pngloss.c:266) */
+    flush_logs(&r);
+    parallel_for(&r, encode_job);      /* 3. encode every output (CPU threads) */
+    flush_logs(&r);
 
-    /* ---- 2. one batched call replaces the per-file optimize_with_rows (reference src/pngloss.c:266) ---- */
-    if (n_gpu) {
-        pngloss_b200_ctx *ctx = NULL;
-        int dev = getenv("PNGLOSS_B200_DEVICE") ? atoi(getenv("PNGLOSS_B200_DEVICE")) : 0;
-        int grc = pngloss_b200_ctx_create(&ctx, dev, NULL);
-        if (grc == 0) {
-            grc = pngloss_b200_optimize_batch(ctx, gpu_jobs, n_gpu, (unsigned)o.strength, (long)o.bleed_divider);
-            if (grc && grc != PNGLOSS_B200_NO_ACCEPTABLE_ROW)
-                fprintf(stderr, "  error: %s\n", pngloss_b200_ctx_error(ctx));
-        } else {
-            fprintf(stderr, "  error: no usable CUDA device %d (pngloss_b200 has no CPU fallback)\n", dev);
-        }
-        for (unsigned k = 0; k < n_gpu; k++) {
-            struct job *j = &jobs[gpu_index[k]];
-            const int st = grc && !gpu_jobs[k].status ? grc : gpu_jobs[k].status;
-            if (st == PNGLOSS_B200_NO_ACCEPTABLE_ROW) {
-                fprintf(stderr, "\naborting because no good row in %s\n", j->filename);   /* reference abort()s */
-                abort();
-            }
-            if (st) j->rc = st == PNGLOSS_B200_OUT_OF_MEMORY ? OUT_OF_MEMORY_ERROR : PNGLOSS_DEVICE_ERROR;
-            else if (o.verbose)
-                fprintf(stderr, "%s:\n  compression complete (%u bytes per pixel)\n", j->filename,
-                        gpu_jobs[k].bytes_per_pixel);
-        }
-        if (ctx) pngloss_b200_ctx_destroy(ctx);
-    }
-
-    /* ---- 3. encode (reference src/pngloss.c:268-300) -------------------------------------------------- */
     unsigned error_count = 0, skipped_count = 0;
     pngloss_error latest_error = SUCCESS;
-    for (unsigned i = 0; i < n; i++) {
-        struct job *j = &jobs[i];
-        if (j->loaded && j->rc == SUCCESS) {
-            if (o.skip_if_larger) j->output.maximum_file_size = j->input.file_size - 1;
-            j->output.chunks = j->input.chunks;
-            j->input.chunks = NULL;
-            j->rc = write_image(&j->output, j->row_filters, j->outname, &o);
-            if (o.verbose) {
-                if (j->rc == SUCCESS) {
-                    fprintf(stderr, "  wrote %luKB file (%.1f%% of original)\n",
-                            ((unsigned long)j->output.file_size + 500UL) / 1000UL,
-                            100.0f * (float)j->output.file_size / (float)j->input.file_size);
-                    if (j->output.metadata_size > 0)
-                        fprintf(stderr, "  copied %dKB of additional PNG metadata\n",
-                                (int)(j->output.metadata_size + 500) / 1000);
-                } else if (j->rc == TOO_LARGE_FILE) {
-                    fprintf(stderr, "  file exceeded maximum size of %luKB\n",
-                            ((unsigned long)j->output.maximum_file_size + 500UL) / 1000UL);
-                }
-            }
-            /* on stdout an empty result would be nasty: send the original instead (reference :286-293) */
-            if (o.using_stdout && j->rc == TOO_LARGE_FILE) {
-                pngloss_error wrc = write_image(&j->input, NULL, j->outname, &o);
-                if (wrc) j->rc = wrc;
-            }
-        }
+    for (unsigned i = 0; i < r.n; i++) {
+        struct job *j = &r.jobs[i];
         if (j->rc) {
             latest_error = j->rc;
             if (j->rc == TOO_LOW_QUALITY || j->rc == TOO_LARGE_FILE) skipped_count++;
@@ -371,7 +538,10 @@ int main(int argc, char *argv[]) {
         rwpng_free_image24(&j->output);
         free(j->row_filters);
         free(j->outname_free);
+        if (j->logf && j->logf != stderr) fclose(j->logf);
+        free(j->log);
     }
+    const unsigned n = r.n;
     if (o.verbose) {
         if (error_count)
             fprintf(stderr, "There were errors compressing %d file%s out of a total of %d file%s.\n", error_count,
@@ -381,8 +551,6 @@ int main(int argc, char *argv[]) {
                     skipped_count == 1 ? "" : "s", n, n == 1 ? "" : "s");
         if (!skipped_count && !error_count) fprintf(stderr, "Compressed %d image%s.\n", n, n == 1 ? "" : "s");
     }
-    free(jobs);
-    free(gpu_jobs);
-    free(gpu_index);
+    free(r.jobs);
     return latest_error;
 }

@@ -62,7 +62,10 @@ def test_cli_batch_of_files_matches_oracle(tmp_path, oracle):
         p = str(tmp_path / f"{key}.png")
         Image.fromarray(rgba, "RGBA").save(p)       # every input is an RGBA PNG; the path narrows it itself
         paths.append(p)
-    r = subprocess.run([CLI, "-v", "-s", "19", "-b", "2", "--", *paths], capture_output=True, text=True)
+    # --jobs / --gpus are additions of this build: CPU threads for PNG decode/encode, files sharded over
+    # all visible GPUs (one on the test box; the sharding itself is host logic)
+    r = subprocess.run([CLI, "-v", "-s", "19", "-b", "2", "--jobs", "3", "--gpus", "0", "--", *paths],
+                       capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert f"Compressed {len(paths)} images." in r.stderr
     for key, rgba in imgs.items():

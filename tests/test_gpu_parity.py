@@ -10,6 +10,9 @@ from golden_cases import case_id, cases, load_input
 
 pytestmark = pytest.mark.gpu
 
+import os as _os
+ROOT_DIR = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+
 
 @pytest.fixture(scope="module")
 def oracle():
@@ -286,6 +289,47 @@ def test_large_host_batch_matches_device_resident_path(ctx, oracle):
         ctx.sync()
         assert np.array_equal(out, work[i]) and np.array_equal(rf, rfs[i]), i
     batch.close()
+    ctx.set_lanes(0)
+
+
+def test_batch_larger_than_memory_budget_is_grouped(oracle):
+    """A host batch that does not fit the device at once runs as consecutive groups
+    (PNGLOSS_B200_MEM_BUDGET_MB shrinks the budget so that small inputs exercise it)."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import pngloss_b200
+from checkers import Oracle
+o = Oracle()
+imgs = [o.synth(200, 120, 300 + i) for i in range(9)]          # ~0.3 MB of device memory each
+work = [im.copy() for im in imgs]
+rfs = [np.zeros(120, np.uint8) for _ in imgs]
+ctx = pngloss_b200.Context(0)
+res = ctx.optimize_batch(work, rfs, 20, 2)
+for im, got, rf, r in zip(imgs, work, rfs, res):
+    px, want_rf = o.optimize(im, 20, 2, True)
+    assert r["status"] == 0 and np.array_equal(got, px) and np.array_equal(rf, want_rf)
+print("grouped ok")
+""" % (ROOT_DIR, os.path.join(ROOT_DIR, "tests"))
+    env = dict(os.environ, PNGLOSS_B200_MEM_BUDGET_MB="1")        # 1 MB: three images per group
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert r.returncode == 0 and "grouped ok" in r.stdout, r.stderr
+
+
+def test_full_width_8192_matches_oracle(ctx, oracle):
+    """BASELINE configs[4] uses 8192-pixel rows: full width, a strip of rows, exact against the oracle."""
+    img = oracle.synth(8192, 48, 1000)
+    want_px, want_rf = oracle.optimize(img, 20, 2, True)
+    for lanes in (8, 1):
+        ctx.set_lanes(lanes)
+        got = img.copy()
+        rf = np.zeros(48, np.uint8)
+        res = ctx.optimize_batch([got], [rf], 20, 2)
+        assert res[0]["status"] == 0
+        assert np.array_equal(got, want_px) and np.array_equal(rf, want_rf), lanes
     ctx.set_lanes(0)
 
 
