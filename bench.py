@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--strength", type=int, default=20)
     ap.add_argument("--bleed", type=int, default=2)
     ap.add_argument("--lanes", type=int, default=0, help="lanes per channel of K2 (0 = library default)")
+    ap.add_argument("--bm", type=int, default=-1,
+                    help="K2 candidate choice: 1 bucket maxima, 0 scan only, -1 library default")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows per core of the CPU sample (0 = auto)")
@@ -220,6 +222,7 @@ def main():
     ctx = pngloss_b200.Context(local_rank)
     if a.lanes:
         ctx.set_lanes(a.lanes)
+    ctx.set_bucket_maxima(a.bm)
     n, w, h = a.images, a.width, a.height
     px_per_step_rank = n * w * h
 
@@ -349,6 +352,8 @@ def main():
                        "strength": a.strength, "bleed": a.bleed,
                        "l2": f"inputs {n * w * h * 4 / 1e9:.1f} GB per GPU >> 126 MB L2, no flush needed",
                        "k2_lanes_per_channel": 8 // info["images_per_cta"],
+                       "k2_candidate_choice": ("bucket maxima" if (a.bm == 1 or (a.bm < 0 and a.strength >= 15))
+                                               else "scan"),
                        "k2_ctas": info["k2_ctas"], "k2_smem_bytes": info["k2_smem_bytes"],
                        "collective": "nccl all_reduce 256 x u64 per step" if world > 1 else "none (1 GPU)",
                        "wall_ms_per_step": wall_ms / a.steps},

@@ -77,6 +77,10 @@ const char *pngloss_b200_ctx_error(const pngloss_b200_ctx *ctx);
 /* Lane mapping of the quantise kernel: lanes per colour channel = 8, 4, 2 or 1, i.e. 1, 2, 4 or 8
  * images per CTA; 0 = choose from the batch size.  A tuning knob, results never depend on it. */
 int pngloss_b200_ctx_set_lanes(pngloss_b200_ctx *ctx, int lanes_per_channel);
+/* Candidate choice of the quantise kernel: 1 = per-band winner table ("bucket maxima") with the scan as
+ * fall-back, 0 = scan every band, -1 = choose from the strength (default).  A tuning knob, results
+ * never depend on it. */
+int pngloss_b200_ctx_set_bucket_maxima(pngloss_b200_ctx *ctx, int mode);
 /* CUDA-event stopwatch on the context's stream (what bench.py times with). */
 int pngloss_b200_ctx_timer_start(pngloss_b200_ctx *ctx);
 int pngloss_b200_ctx_timer_stop(pngloss_b200_ctx *ctx, float *milliseconds);

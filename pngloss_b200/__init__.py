@@ -27,7 +27,7 @@ NO_ACCEPTABLE_ROW = 41
 EXPORTS = [
     "optimize_with_rows", "optimize_with_stride", "optimizeForAverageFilter", "optimize_image",
     "pngloss_b200_device_count", "pngloss_b200_ctx_create", "pngloss_b200_ctx_destroy",
-    "pngloss_b200_ctx_error", "pngloss_b200_ctx_set_lanes", "pngloss_b200_ctx_timer_start",
+    "pngloss_b200_ctx_error", "pngloss_b200_ctx_set_lanes", "pngloss_b200_ctx_set_bucket_maxima", "pngloss_b200_ctx_timer_start",
     "pngloss_b200_ctx_timer_stop", "pngloss_b200_ctx_sync", "pngloss_b200_host_alloc",
     "pngloss_b200_host_free", "pngloss_b200_optimize_batch", "pngloss_b200_batch_create",
     "pngloss_b200_batch_destroy", "pngloss_b200_batch_set_mode", "pngloss_b200_batch_upload",
@@ -90,6 +90,7 @@ def load_library() -> ctypes.CDLL:
     L.pngloss_b200_ctx_error.argtypes = [vp]
     L.pngloss_b200_ctx_error.restype = ctypes.c_char_p
     L.pngloss_b200_ctx_set_lanes.argtypes = [vp, i32]
+    L.pngloss_b200_ctx_set_bucket_maxima.argtypes = [vp, i32]
     L.pngloss_b200_ctx_timer_start.argtypes = [vp]
     L.pngloss_b200_ctx_timer_stop.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     L.pngloss_b200_ctx_sync.argtypes = [vp]
@@ -191,6 +192,10 @@ class Context:
 
     def set_lanes(self, lanes_per_channel: int):
         self._check(self.lib.pngloss_b200_ctx_set_lanes(self.handle, lanes_per_channel))
+
+    def set_bucket_maxima(self, mode: int):
+        """K2's candidate choice: 1 winner table + scan fall-back, 0 scan only, -1 from the strength."""
+        self._check(self.lib.pngloss_b200_ctx_set_bucket_maxima(self.handle, mode))
 
     def timer_start(self):
         self._check(self.lib.pngloss_b200_ctx_timer_start(self.handle))

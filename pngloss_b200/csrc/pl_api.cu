@@ -21,6 +21,7 @@ struct pngloss_b200_ctx {
     bool own_stream = false;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     int lpc = 0;
+    int bm = -1;   // bucket-maxima variant of K2: -1 choose from the strength, 0 off, 1 on
     char err[512] = {0};
     pngloss_b200_batch *cached = nullptr;   // last batch built by pngloss_b200_optimize_batch
 };
@@ -117,6 +118,12 @@ extern "C" int pngloss_b200_ctx_set_lanes(pngloss_b200_ctx *ctx, int lpc) {
     if (!ctx || !(lpc == 0 || lpc == 1 || lpc == 2 || lpc == 4 || lpc == 8))
         return PNGLOSS_B200_INVALID_ARGUMENT;
     ctx->lpc = lpc;
+    return PNGLOSS_B200_SUCCESS;
+}
+
+extern "C" int pngloss_b200_ctx_set_bucket_maxima(pngloss_b200_ctx *ctx, int mode) {
+    if (!ctx || mode < -1 || mode > 1) return PNGLOSS_B200_INVALID_ARGUMENT;
+    ctx->bm = mode;
     return PNGLOSS_B200_SUCCESS;
 }
 
@@ -317,23 +324,28 @@ extern "C" int pngloss_b200_batch_synth(pngloss_b200_batch *b, size_t i, uint64_
     return PNGLOSS_B200_SUCCESS;
 }
 
-template <int LPC>
+template <int LPC, bool BM>
 static int launch_k2(pngloss_b200_batch *b, int nblocks, unsigned strength, long bleed) {
     pngloss_b200_ctx *ctx = b->ctx;
     static bool attr_set[16] = {false};
-    const size_t smem = sizeof(PlCtaSmem<LPC>) + PL_K2_SMEM_ALIGN;   // slack for the in-kernel alignment
+    const size_t smem = sizeof(PlCtaSmem<LPC, BM>) + PL_K2_SMEM_ALIGN;   // slack for the in-kernel alignment
     if (!attr_set[ctx->device & 15]) {
-        PL_CUDA(ctx, cudaFuncSetAttribute(pl_k2_quantize<LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PL_CUDA(ctx, cudaFuncSetAttribute(pl_k2_quantize<LPC, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem));
         attr_set[ctx->device & 15] = true;
     }
-    pl_k2_quantize<LPC><<<nblocks, PL_K2_THREADS, smem, b->stream>>>(b->dimgs, b->dslots, (int)strength,
-                                                                      (int)bleed);
+    pl_k2_quantize<LPC, BM><<<nblocks, PL_K2_THREADS, smem, b->stream>>>(b->dimgs, b->dslots, (int)strength,
+                                                                          (int)bleed);
     PL_CUDA(ctx, cudaGetLastError());
     b->info[0] = (uint32_t)nblocks;
     b->info[1] = (uint32_t)PlCfg<LPC>::CPW;
     b->info[2] = (uint32_t)smem;
     return PNGLOSS_B200_SUCCESS;
+}
+template <int LPC>
+static int launch_k2(pngloss_b200_batch *b, int nblocks, unsigned strength, long bleed, bool bm) {
+    return bm ? launch_k2<LPC, true>(b, nblocks, strength, bleed)
+              : launch_k2<LPC, false>(b, nblocks, strength, bleed);
 }
 
 // Lane mapping by batch size, from the B200 sweeps in profiles/ (3840-wide images): with few images
@@ -387,12 +399,15 @@ extern "C" int pngloss_b200_batch_run(pngloss_b200_batch *b, unsigned strength, 
     pl_k1_orig_hist<<<(unsigned)(b->n * slices), PL_K1_THREADS, 0, b->stream>>>(b->dimgs, slices);
     PL_CUDA(ctx, cudaGetLastError());
     PL_CUDA(ctx, cudaEventRecord(b->ev[1], b->stream));
+    // Bucket maxima replace the per-byte candidate scan by a table look-up; the table only exists for
+    // strength + 1 >= PL_BM_MIN_STEP (at lower strengths the scan is short anyway).
+    const bool bm = ctx->bm >= 0 ? ctx->bm != 0 : strength + 1 >= PL_BM_MIN_STEP;
     int rc;
     switch (lpc) {
-    case 8: rc = launch_k2<8>(b, nblocks, strength, bleed); break;
-    case 4: rc = launch_k2<4>(b, nblocks, strength, bleed); break;
-    case 2: rc = launch_k2<2>(b, nblocks, strength, bleed); break;
-    default: rc = launch_k2<1>(b, nblocks, strength, bleed); break;
+    case 8: rc = launch_k2<8>(b, nblocks, strength, bleed, bm); break;
+    case 4: rc = launch_k2<4>(b, nblocks, strength, bleed, bm); break;
+    case 2: rc = launch_k2<2>(b, nblocks, strength, bleed, bm); break;
+    default: rc = launch_k2<1>(b, nblocks, strength, bleed, bm); break;
     }
     if (rc) return rc;
     PL_CUDA(ctx, cudaEventRecord(b->ev[2], b->stream));

@@ -25,7 +25,11 @@ extern unsigned long long pl_emu_counters[8];
 #else
 #define PL_EMU_COUNT(slot) ((void)0)
 #endif
-enum { PL_CNT_TAPS_TABLE = 0, PL_CNT_TAPS_COMPUTED = 1, PL_CNT_FIXUP_REPLAY = 2, PL_CNT_FIXUP_SKIPPED = 3 };
+enum {
+    PL_CNT_TAPS_TABLE = 0, PL_CNT_TAPS_COMPUTED = 1, PL_CNT_FIXUP_REPLAY = 2, PL_CNT_FIXUP_SKIPPED = 3,
+    // bucket-maxima variant: bytes answered by the look-up / by the scan, table updates by +1 / by max
+    PL_CNT_BM_LOOKUP = 4, PL_CNT_BM_SCAN = 5, PL_CNT_BM_FASTUPD = 6, PL_CNT_BM_GENERAL = 7
+};
 
 // ---- cp.async (LDGSTS): global -> shared without a register round trip ---------------------------
 // 4- and 8-byte forms only exist as .ca; the sources are rows this CTA itself wrote (same SM, so

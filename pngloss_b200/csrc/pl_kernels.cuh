@@ -173,7 +173,12 @@ struct PlWarpSmem {
 #define PL_K2_SMEM_ALIGN 2048
 #define PL_DLUT_HALF 512   /* the Sierra tap table covers error values -512 .. 511 (see pl_pack_taps) */
 
-template <int LPC>
+// Bucket-maxima variant (BM): number of entries of PlCtaSmem::bmk per (chain, filter).  Buckets exist
+// for strength + 1 >= 16 (see pl_bm_counts), which gives at most 128/16 + 129/16 = 16 of them.
+#define PL_BM_MAX 16
+#define PL_BM_MIN_STEP 16
+
+template <int LPC, bool BM = false>
 struct PlCtaSmem {
     // Per chain and symbol one 64-bit entry that is already most of a candidate key: high word = the
     // running symbol_frequency, low word = rank of original_frequency[filter][symbol] << 10.
@@ -183,6 +188,9 @@ struct PlCtaSmem {
     unsigned long long hk[PlCfg<LPC>::CPW][PL_FILTERS * 256];
     unsigned long long dlut[PlCfg<LPC>::DLUT ? 2 * PL_DLUT_HALF : 1];   // packed Sierra taps by error value
     uint32_t base[PlCfg<LPC>::CPW][256];              // symbol_frequency at the start of the row
+    // BM: per chain, filter and band ("bucket") of the symbol axis the candidate key of the symbol that
+    // currently wins the choice inside that band (see pl_row_pass)
+    unsigned long long bmk[BM ? PlCfg<LPC>::CPW : 1][BM ? PL_FILTERS : 1][BM ? PL_BM_MAX : 1];
     unsigned long long cost[PlCfg<LPC>::CPW][PL_FILTERS];
     PlImageDev img[PlCfg<LPC>::CPW];
     int win[PlCfg<LPC>::CPW];
@@ -267,8 +275,38 @@ __device__ __forceinline__ unsigned pl_key_low(bool exact, int pos) {
 }
 #define PL_KEY_RANK_MASK (~((1ull << PL_KEY_RANK_SHIFT) - 1ull))   /* count + rank fields */
 
-template <int LPC>
-__device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC> &sm, const PlChain &cn, int F,
+// ---- bucket maxima (BM variant) ------------------------------------------------------------------------
+// Before clamping, the band of admissible symbols of a byte (reference src/optimize_state.c:186-193) is
+// one of a fixed set of intervals of the symbol axis: [k step, k step + q] for want >= 0 and
+// [-k step - q, -k step] for want < 0 (step = q + 1).  Instead of scanning the q + 1 candidates of every
+// byte, the BM variant keeps, per chain and filter, the candidate key of the current winner of every such
+// interval that lies inside [-128, 127] (a "bucket") and looks it up:
+//   * table index: non-negative buckets 0 .. KP-1, then negative buckets KP .. KP+KN-1;
+//   * symbol 0 ends both zero bands; it is a member of bucket 0 only - bucket KP covers [-q, -1] and a
+//     look-up of the band [-q, 0] adds symbol 0 by hand - so that every symbol has at most one bucket;
+//   * key layout as below, position field relative to the first symbol of the bucket, exact bit clear;
+//   * symbol counts only grow, so "maximum of every key the bucket's symbols ever had" is the current
+//     winner: the table is kept up to date by a 64-bit max (or, when the chosen symbol already is the
+//     winner of its bucket, by adding 1 to the count field);
+//   * a band clamped to the byte range is a sub-interval of its bucket: if the bucket winner lies
+//     inside, it also wins the sub-interval; if not - or if the band reaches beyond [-128, 127] - the
+//     byte falls back to the candidate scan.
+struct PlBm {
+    int KP, KN;
+};
+__device__ __forceinline__ PlBm pl_bm_counts(int step) {
+    PlBm b;
+    b.KP = step >= PL_BM_MIN_STEP ? 128 / step : 0;   // (k + 1) step - 1 <= 127
+    b.KN = step >= PL_BM_MIN_STEP ? 129 / step : 0;   // k step + q <= 128
+    return b;
+}
+// first symbol of bucket t
+__device__ __forceinline__ int pl_bm_low(const PlBm &b, int t, int step) {
+    return t < b.KP ? t * step : -(t - b.KP) * step - (step - 1);
+}
+
+template <int LPC, bool BM>
+__device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC, BM> &sm, const PlChain &cn, int F,
                                                           int W, int y, int parity, int prev_w,
                                                           bool adaptive, unsigned bleed_magic) {
     typedef PlCfg<LPC> C;
@@ -318,6 +356,28 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC> &sm, co
     int left = 0, aprev = 0;
     unsigned long long derr = 0;
     unsigned as0 = 0, as1 = 0, as2 = 0, as3 = 0, as4 = 0;
+
+    // BM: the histogram of this candidate was just cloned from the previous row's winner (or restored
+    // for a retry at another strength) and the tie-break rank differs per filter, so the bucket winners
+    // are rebuilt at the start of every pass; the lanes of a chain share its KP + KN buckets.
+    const PlBm bmc = pl_bm_counts(BM ? step : 0);
+    unsigned long long *bmrow = sm.bmk[BM ? ci : 0][BM ? F : 0];
+    if (BM) {
+        if (live) {
+            for (int t = gl; t < bmc.KP + bmc.KN; t += C::GROUP) {
+                const int lo_t = pl_bm_low(bmc, t, step);
+                const int np = t == bmc.KP ? q : q + 1;   // bucket KP leaves symbol 0 to bucket 0
+                unsigned long long best = 0;
+                for (int p = 0; p < np; p++) {
+                    const unsigned long long key =
+                        pl_hk_load(hkt, (unsigned)(lo_t + p + rot) * 8u) | (unsigned)(511 - p);
+                    best = key > best ? key : best;
+                }
+                bmrow[t] = best;
+            }
+        }
+        __syncwarp();
+    }
 
     const int ntiles = (W + C::TP - 1) / C::TP;
     // tile loader: lane (ci, gl) fetches pixel x0 + gl of its chain
@@ -376,36 +436,70 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC> &sm, co
             int here = o + pl_sext16(a0);
             const int want = here - pred;
             const unsigned m = (unsigned)(want < 0 ? -want : want);
-            const int r = (int)(m - pl_udiv_magic(m, step_magic) * (unsigned)step);
-            int lo = want + (want < 0 ? r - q : -r);
-            int hi = lo + q;
+            const unsigned kq = pl_udiv_magic(m, step_magic);   // which band, counted from zero
+            const int r = (int)(m - kq * (unsigned)step);
+            const int lo_u = want + (want < 0 ? r - q : -r);    // first symbol of the band before clamping
             // clamp (:195-210): symbol + predicted must be a byte.  The reference clamps lo from below
             // and hi from above and collapses an emptied band onto the saturated value, which is the
             // same as clamping both ends to [-predicted, 255 - predicted].
             const int smin = -pred, smax = 255 - pred;
-            lo = min(max(lo, smin), smax);
-            hi = min(max(hi, smin), smax);
+            int lo = min(max(lo_u, smin), smax);
+            int hi = min(max(lo_u + q, smin), smax);
             if (transp) {   // fully transparent stays transparent (:158-164): the only symbol is 0 - predicted
                 here = 0;
                 lo = hi = ex = smin;
             }
             const int span = act ? hi - lo : -1;
 
+            unsigned long long acc[C::NACC];
+#pragma unroll
+            for (int k = 0; k < C::NACC; k++) acc[k] = 0;
+
+            // ---- BM: look the band's winner up ----------------------------------------------------
+            bool need_scan = true;
+            int tl = 0;                  // bucket of the unclamped band
+            int wsym_l = 0x7fffffff;     // the symbol bucket tl currently holds (none: no such bucket)
+            bool zero_w0 = false;        // symbol 0 currently wins bucket 0
+            if (BM) {
+                const bool neg = want < 0;
+                const bool tvalid = kq < (unsigned)(neg ? bmc.KN : bmc.KP);
+                tl = tvalid ? (int)kq + (neg ? bmc.KP : 0) : 0;
+                unsigned long long wk = *(volatile unsigned long long *)&bmrow[tl];
+                const unsigned w0low = *(volatile unsigned *)&bmrow[0];
+                zero_w0 = bmc.KP > 0 && (w0low & 511u) == 511u;
+                if (tvalid) wsym_l = lo_u + 511 - (int)((unsigned)wk & 511u);
+                if (neg && kq == 0) {   // band [-q, 0]: symbol 0 lives in bucket 0, add it by hand
+                    const unsigned long long k0 = pl_hk_load(hkt, (unsigned)rot * 8u) | (unsigned)(511 - q);
+                    wk = k0 > wk ? k0 : wk;
+                }
+                const int wsym = lo_u + 511 - (int)((unsigned)wk & 511u);
+                const bool inr = tvalid && wsym >= lo && wsym <= hi;
+                // position field relative to the clamped band: 511 - (wsym - lo)
+                if (act && inr) acc[0] = wk + (unsigned long long)(unsigned)(lo - lo_u);
+                // a band of one symbol that is the exact symbol is covered by the exact candidate below
+                need_scan = act && !inr && !(span == 0 && ex == lo);
+#ifdef PL_SIMT_EMU
+                // path statistics, per warp iteration: does any lane of the warp scan?
+                if (__any_sync(PL_FULL, need_scan)) PL_EMU_COUNT(PL_CNT_BM_SCAN);
+                else PL_EMU_COUNT(PL_CNT_BM_LOOKUP);
+#endif
+            }
+
             // ---- candidate scan against the histogram at the start of the pixel ---------------
             // Every lane looks at candidates sub, sub + LPC, ...; the trip count comes from the
             // strength (warp-uniform), candidates beyond the clamped band are predicated off, and the
             // body is unrolled so that the independent shared-memory loads are in flight together.
             // NACC running maxima (merged after the scan) keep the compare chain short where a lane looks
-            // at many candidates
-            unsigned long long acc[C::NACC];
-#pragma unroll
-            for (int k = 0; k < C::NACC; k++) acc[k] = 0;
-            {
+            // at many candidates.  (BM: only the bytes whose look-up failed come here; need_scan is the
+            // same in all lanes of a channel group and the block contains no warp-level operation.)
+            if (!BM || need_scan) {
                 const int jl = (span - sub) >> C::LOG2LPC;          // last valid j of this lane (-1: none)
                 const unsigned off0 = (unsigned)(lo + sub + rot) * 8u;   // byte offset of candidate j = 0
                 const unsigned low0 = 511u - (unsigned)sub;          // its "511 - pos" field
                 const int jx = ex - lo - sub;                        // j * LPC of the exact symbol, if mine
-                for (int j0 = 0; j0 < jmax; j0 += C::UNR) {
+                // (BM: only this lane's own candidates - the block runs diverged anyway and a clamped band
+                // is usually short)
+                for (int j0 = 0; j0 < (BM ? jl + 1 : jmax); j0 += C::UNR) {
                     // per-chunk bases, so that each candidate below only adds compile-time constants
                     const unsigned off_c = off0 + (unsigned)(j0 * LPC * 8);
                     const unsigned low_c = low0 - (unsigned)(j0 * LPC);
@@ -419,15 +513,15 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC> &sm, co
                         a = (u <= jl_c && key > a) ? key : a;
                     }
                 }
-                if (C::EXSEP) {
-                    // the exact symbol, with its bonus bit; every lane of the group may add it (max is
-                    // idempotent)
-                    const int pos = ex - lo;
-                    const unsigned long long key =
-                        pl_hk_load(hkt, (unsigned)(ex + rot) * 8u) | pl_key_low(true, pos & 255);
-                    unsigned long long &a = acc[C::NACC - 1];
-                    a = (pos >= 0 && pos <= span && key > a) ? key : a;
-                }
+            }
+            if (C::EXSEP || BM) {
+                // the exact symbol, with its bonus bit; every lane of the group may add it (max is
+                // idempotent)
+                const int pos = ex - lo;
+                const unsigned long long key =
+                    pl_hk_load(hkt, (unsigned)(ex + rot) * 8u) | pl_key_low(true, pos & 255);
+                unsigned long long &a = acc[C::NACC - 1];
+                a = (pos >= 0 && pos <= span && key > a) ? key : a;
             }
 #pragma unroll
             for (int k = C::NACC / 2; k >= 1; k >>= 1)
@@ -466,7 +560,23 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC> &sm, co
                                 (pos != bpos) & ((theirs >> 8) + 3u >= bf);
                 }
             }
-            if (!__any_sync(PL_FULL, conflict)) {
+            // BM: with the provisional winner final, is the bucket table kept current by a plain
+            // "count + 1" (the chosen symbol is the winner its bucket already holds)?
+            bool hit_l = false, bm_slow = false;
+            if (BM) {
+                const int psym = lo + bpos;
+                hit_l = psym == wsym_l;
+                bm_slow = act && !(hit_l || (psym == 0 && zero_w0));
+            }
+            bool general = false;   // BM: the bucket table needs the general (64-bit max) update
+            bool replay;
+            if (!BM) {
+                replay = __any_sync(PL_FULL, conflict);
+            } else {   // one vote on the fast path, a second one only where the first said "slow"
+                general = __any_sync(PL_FULL, conflict || bm_slow);
+                replay = general && __any_sync(PL_FULL, conflict);
+            }
+            if (!replay) {
                 PL_EMU_COUNT(PL_CNT_FIXUP_SKIPPED);
             } else {
                 PL_EMU_COUNT(PL_CNT_FIXUP_REPLAY);
@@ -498,7 +608,27 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC> &sm, co
             const int sym = lo + bpos;
             const int back = act ? sym + pred : 0;
             if (act && sub == 0) {
-                atomicAdd((unsigned *)&hk[(unsigned)(sym + rot) & 255u] + 1, 1u);   // high word = count
+                unsigned *cnt = (unsigned *)&hk[(unsigned)(sym + rot) & 255u] + 1;   // high word = count
+                if (!BM) {
+                    atomicAdd(cnt, 1u);
+                } else if (!general) {
+                    PL_EMU_COUNT(PL_CNT_BM_FASTUPD);
+                    atomicAdd(cnt, 1u);
+                    atomicAdd((unsigned *)&bmrow[hit_l ? tl : 0] + 1, 1u);
+                } else {
+                    PL_EMU_COUNT(PL_CNT_BM_GENERAL);
+                    // the symbol's new key enters its bucket (if it has one) by a 64-bit maximum
+                    const unsigned now = atomicAdd(cnt, 1u) + 1u;
+                    const int s8 = (int)(signed char)sym;   // the histogram bin, as a symbol in [-128, 127]
+                    const unsigned ks = pl_udiv_magic((unsigned)(s8 < 0 ? -s8 : s8), step_magic);
+                    if (ks < (unsigned)(s8 < 0 ? bmc.KN : bmc.KP)) {
+                        const int ts = (int)ks + (s8 < 0 ? bmc.KP : 0);
+                        const int pos_b = s8 - pl_bm_low(bmc, ts, step);
+                        const unsigned long long nk = ((unsigned long long)now << 32) |
+                                                      ((unsigned)bkey & ~1023u) | (unsigned)(511 - pos_b);
+                        atomicMax(&bmrow[ts], nk);
+                    }
+                }
                 ((unsigned char *)&ws.back[ci][i + 1])[ch] = (unsigned char)back;
             }
             left = back;
@@ -642,13 +772,13 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC> &sm, co
     return cost;
 }
 
-template <int LPC>
+template <int LPC, bool BM>
 __global__ void __launch_bounds__(PL_K2_THREADS, PL_K2_MIN_BLOCKS(LPC))
 pl_k2_quantize(const PlImageDev *imgs, const int *slots, int strength, int bleed) {
     typedef PlCfg<LPC> C;
     PL_DYN_SMEM(smem_raw);
     // 2 KB alignment for the histogram tables (the launch reserves PL_K2_SMEM_ALIGN spare bytes)
-    PlCtaSmem<LPC> &sm = *(PlCtaSmem<LPC> *)pl_align_shared(smem_raw, PL_K2_SMEM_ALIGN);
+    PlCtaSmem<LPC, BM> &sm = *(PlCtaSmem<LPC, BM> *)pl_align_shared(smem_raw, PL_K2_SMEM_ALIGN);
     const int tid = threadIdx.x;
     // Warps 0 and 4 of a CTA land on the same SM sub-partition (warp id % 4) and are measurably the
     // slow pair when few CTAs share an SM (profiles/r1_filter_warp_busy.txt), so they get the two
@@ -756,7 +886,7 @@ pl_k2_quantize(const PlImageDev *imgs, const int *slots, int strength, int bleed
             const long long prof_t0 = clock64();
 #endif
             const unsigned long long cost =
-                pl_row_pass<LPC>(sm, cn, F, W, y, y & 1, prev_w, adaptive, bleed_magic);
+                pl_row_pass<LPC, BM>(sm, cn, F, W, y, y & 1, prev_w, adaptive, bleed_magic);
 #ifdef PL_K2_PROFILE
             prof_busy += (unsigned long long)(clock64() - prof_t0);
 #endif

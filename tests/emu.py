@@ -24,7 +24,8 @@ class Emu:
         self.lib.emu_synth.restype = None
 
     def optimize(self, imgs, strength, bleed, adaptive_all, lpc):
-        """imgs: list of equally sized (h, w, 4) uint8 arrays -> dict of outputs."""
+        """imgs: list of equally sized (h, w, 4) uint8 arrays -> dict of outputs.
+        lpc: lanes per channel (8, 4, 2, 1), + 16 selects the bucket-maxima variant of K2."""
         n = len(imgs)
         h, w, _ = imgs[0].shape
         buf = np.ascontiguousarray(np.stack(imgs)).copy()
@@ -44,7 +45,8 @@ class Emu:
         """Sierra taps from the table / computed, channel fix-up replays / skips executed so far (per lane)."""
         out = (ctypes.c_ulonglong * 8)()
         self.lib.emu_counters(out)
-        return dict(taps_table=out[0], taps_computed=out[1], fixup_replay=out[2], fixup_skipped=out[3])
+        return dict(taps_table=out[0], taps_computed=out[1], fixup_replay=out[2], fixup_skipped=out[3],
+                    bm_lookup=out[4], bm_scan=out[5], bm_fast_update=out[6], bm_general_update=out[7])
 
     def synth(self, w, h, seed):
         a = np.zeros((h, w, 4), np.uint8)

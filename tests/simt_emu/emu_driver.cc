@@ -7,9 +7,13 @@
 
 template <int LPC>
 static void run_k2(const PlImageDev *imgs, const int *slots, int nblocks, int strength, int bleed,
-                   int) {
-    simt::launch([&] { pl_k2_quantize<LPC>(imgs, slots, strength, bleed); },
-                 dim3(nblocks), dim3(PL_K2_THREADS), sizeof(PlCtaSmem<LPC>) + PL_K2_SMEM_ALIGN);
+                   bool bm) {
+    if (bm)
+        simt::launch([&] { pl_k2_quantize<LPC, true>(imgs, slots, strength, bleed); },
+                     dim3(nblocks), dim3(PL_K2_THREADS), sizeof(PlCtaSmem<LPC, true>) + PL_K2_SMEM_ALIGN);
+    else
+        simt::launch([&] { pl_k2_quantize<LPC, false>(imgs, slots, strength, bleed); },
+                     dim3(nblocks), dim3(PL_K2_THREADS), sizeof(PlCtaSmem<LPC, false>) + PL_K2_SMEM_ALIGN);
 }
 
 extern "C" int emu_optimize(unsigned char *rgba, int n, uint32_t w, uint32_t h,
@@ -47,15 +51,18 @@ extern "C" int emu_optimize(unsigned char *rgba, int n, uint32_t w, uint32_t h,
     simt::launch([&] { pl_k1_orig_hist(dimgs, k1_slices); }, dim3(k1_slices * n), dim3(PL_K1_THREADS), 0);
     if (chan_hist_out) memcpy(chan_hist_out, chan.data(), chan.size() * sizeof(uint32_t));
 
+    // lpc: lanes per channel (8, 4, 2, 1), + 16 for the bucket-maxima variant of K2
+    const bool bm = (lpc & 16) != 0;
+    lpc &= 15;
     const int cpw = 8 / lpc;
     const int nblocks = (n + cpw - 1) / cpw;
     std::vector<int> slots((size_t)nblocks * cpw, -1);
     for (int i = 0; i < n; i++) slots[i] = i;
     switch (lpc) {
-    case 8: run_k2<8>(dimgs, slots.data(), nblocks, strength, bleed, adaptive_all); break;
-    case 4: run_k2<4>(dimgs, slots.data(), nblocks, strength, bleed, adaptive_all); break;
-    case 2: run_k2<2>(dimgs, slots.data(), nblocks, strength, bleed, adaptive_all); break;
-    case 1: run_k2<1>(dimgs, slots.data(), nblocks, strength, bleed, adaptive_all); break;
+    case 8: run_k2<8>(dimgs, slots.data(), nblocks, strength, bleed, bm); break;
+    case 4: run_k2<4>(dimgs, slots.data(), nblocks, strength, bleed, bm); break;
+    case 2: run_k2<2>(dimgs, slots.data(), nblocks, strength, bleed, bm); break;
+    case 1: run_k2<1>(dimgs, slots.data(), nblocks, strength, bleed, bm); break;
     default: return -1;
     }
     if (batch_hist) {

@@ -46,11 +46,14 @@ def test_golden_through_dropin_entry(oracle, c):
         assert sha16(rf) == c["filt_sha"]
 
 
+@pytest.mark.parametrize("bm", [0, 1], ids=["scan", "bucket-maxima"])
 @pytest.mark.parametrize("lanes", [8, 4, 2, 1])
-def test_golden_batched_all_lane_mappings(ctx, oracle, lanes):
+def test_golden_batched_all_lane_mappings(ctx, oracle, lanes, bm):
     """All small golden cases of one (strength, bleed) in a single batch: mixed sizes, mixed colour
-    modes, mixed row_filters/NULL, every lane mapping of the quantise kernel."""
+    modes, mixed row_filters/NULL, every lane mapping and both candidate-choice variants of the
+    quantise kernel."""
     ctx.set_lanes(lanes)
+    ctx.set_bucket_maxima(bm)
     groups = {}
     for c in cases("small"):
         groups.setdefault((c["strength"], c["bleed"]), []).append(c)
@@ -64,6 +67,7 @@ def test_golden_batched_all_lane_mappings(ctx, oracle, lanes):
             if c["filters"]:
                 assert sha16(rf) == c["filt_sha"], case_id(c)
     ctx.set_lanes(0)
+    ctx.set_bucket_maxima(-1)
 
 
 def test_golden_large_4k_and_1080p(ctx, oracle):
@@ -113,6 +117,7 @@ def test_random_inputs_match_oracle(ctx, oracle):
         work = [im.copy() for im in imgs]
         rfs = [np.zeros(im.shape[0], np.uint8) if nf else None for im, nf in zip(imgs, params)]
         ctx.set_lanes([8, 4, 2, 1][rep % 4])
+        ctx.set_bucket_maxima([1, 0, -1][rep % 3])
         res = ctx.optimize_batch(work, rfs, s, b)
         for im, got, rf, nf, r in zip(imgs, work, rfs, params, res):
             want_px, want_rf, tr = oracle.optimize(im, s, b, nf, trace=True)
@@ -122,6 +127,7 @@ def test_random_inputs_match_oracle(ctx, oracle):
                 assert np.array_equal(rf, want_rf), (rep, im.shape, s, b, nf)
             assert r["retried_rows"] == int((s - tr["row_strength"].astype(int)).sum())
     ctx.set_lanes(0)
+    ctx.set_bucket_maxima(-1)
 
 
 def test_retry_path_on_device(ctx, oracle):
@@ -130,8 +136,9 @@ def test_retry_path_on_device(ctx, oracle):
     rng = np.random.default_rng(7)
     imgs = [to_bpp(rng.integers(0, 256, (3, 5, 4), dtype=np.uint8), int(rng.integers(1, 5)))
             for _ in range(64)]
-    for lanes in (8, 1):
+    for lanes, bm in ((8, 0), (1, 0), (1, 1), (2, 1)):
         ctx.set_lanes(lanes)
+        ctx.set_bucket_maxima(bm)
         work = [im.copy() for im in imgs]
         res = ctx.optimize_batch(work, None, 20, 2)
         total_retries = 0
@@ -142,6 +149,7 @@ def test_retry_path_on_device(ctx, oracle):
             total_retries += r["retried_rows"]
         assert total_retries > 0
     ctx.set_lanes(0)
+    ctx.set_bucket_maxima(-1)
 
 
 def test_secondary_entry_points(oracle):
@@ -323,14 +331,43 @@ def test_full_width_8192_matches_oracle(ctx, oracle):
     """BASELINE configs[4] uses 8192-pixel rows: full width, a strip of rows, exact against the oracle."""
     img = oracle.synth(8192, 48, 1000)
     want_px, want_rf = oracle.optimize(img, 20, 2, True)
-    for lanes in (8, 1):
+    for lanes, bm in ((8, 0), (1, 0), (1, 1), (2, 1), (8, 1)):
         ctx.set_lanes(lanes)
+        ctx.set_bucket_maxima(bm)
         got = img.copy()
         rf = np.zeros(48, np.uint8)
         res = ctx.optimize_batch([got], [rf], 20, 2)
         assert res[0]["status"] == 0
-        assert np.array_equal(got, want_px) and np.array_equal(rf, want_rf), lanes
+        assert np.array_equal(got, want_px) and np.array_equal(rf, want_rf), (lanes, bm)
     ctx.set_lanes(0)
+    ctx.set_bucket_maxima(-1)
+
+
+def test_4k_golden_eight_images_per_cta_bucket_maxima(ctx, oracle):
+    """The bench's kernel variant (one lane per channel, 8 images per CTA, bucket maxima) on the full-size
+    4K golden vector: 8 replicas in one CTA, every one must hash to the reference's output."""
+    c = [c for c in cases("large") if c["src"]["w"] == 3840 and c["strength"] == 20][0]
+    src = c["src"]
+    n = 8
+    ctx.set_lanes(1)
+    ctx.set_bucket_maxima(1)
+    batch = pngloss_b200.Batch(ctx, [src["w"]] * n, [src["h"]] * n)
+    for i in range(n):
+        batch.synth(i, src["seed"])
+    batch.run(c["strength"], c["bleed"])
+    st, bpp, _ = batch.finish()
+    assert (st == 0).all() and (bpp == 4).all()
+    out = np.zeros((src["h"], src["w"], 4), np.uint8)
+    rf = np.zeros(src["h"], np.uint8)
+    for i in range(n):
+        batch.download(i, out, rf)
+        ctx.sync()
+        assert sha16(out) == c["px_sha"] and sha16(rf) == c["filt_sha"], i
+    info = batch.launch_info()
+    assert info["images_per_cta"] == 8 and info["k2_ctas"] == 1
+    batch.close()
+    ctx.set_lanes(0)
+    ctx.set_bucket_maxima(-1)
 
 
 def test_invalid_arguments(ctx):

@@ -53,7 +53,10 @@ CASES = [  # w, h, seed, bpp, strength, bleed, null_filters
 ]
 
 
-@pytest.mark.parametrize("lpc", [8, 4, 2, 1])
+BM = 16   # added to lpc: the bucket-maxima variant of K2 (see emu.py)
+
+
+@pytest.mark.parametrize("lpc", [8, 4, 2, 1, BM + 8, BM + 2, BM + 1])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "w%d-h%d-seed%d-bpp%d-s%d-b%d-null%d" % c)
 def test_emu_single_image(emu, oracle, case, lpc):
     w, h, seed, bpp, s, b, nf = case
@@ -62,14 +65,14 @@ def test_emu_single_image(emu, oracle, case, lpc):
     assert got["status"][0][1] == bpp or (w * h == 1)
 
 
-@pytest.mark.parametrize("lpc", [8, 4, 2, 1])
+@pytest.mark.parametrize("lpc", [8, 4, 2, 1, BM + 4, BM + 1])
 def test_emu_batch_mixed_modes(emu, oracle, lpc):
     """Several images per CTA (CPW = 8/lpc), every bytes-per-pixel mode, partially filled last CTA."""
     imgs = [to_bpp(oracle.synth(29, 6, 100 + i), (i % 4) + 1) for i in range(11)]
     compare(emu, oracle, imgs, 20, 2, False, lpc)
 
 
-@pytest.mark.parametrize("lpc", [8, 2, 1])
+@pytest.mark.parametrize("lpc", [8, 2, 1, BM + 2, BM + 1])
 def test_emu_retry_path(emu, oracle, lpc):
     """row_filters == NULL on tiny noisy images makes the libpng-heuristic check reject all five
     candidates now and then, which exercises the lower-strength retry (reference
@@ -95,7 +98,7 @@ def test_emu_noise_and_ties(emu, oracle):
     noise = rng.integers(0, 256, (6, 21, 4), dtype=np.uint8)
     holes = noise.copy()
     holes[rng.random((6, 21)) < 0.3, 3] = 0                            # fully transparent pixels
-    for lpc in (8, 2):
+    for lpc in (8, 2, BM + 1, BM + 4):
         compare(emu, oracle, [few, noise, holes, to_bpp(holes, 2)], 19, 2, False, lpc)
         compare(emu, oracle, [few, noise, holes, to_bpp(holes, 2)], 200, 1, True, lpc)
 
@@ -112,6 +115,27 @@ def test_emu_both_variants_of_each_path_ran(emu, oracle):
     compare(emu, oracle, [noisy], 255, 1, False, 8)          # errors beyond the table range
     after = emu.counters()
     for key in ("taps_table", "taps_computed", "fixup_replay", "fixup_skipped"):
+        assert after[key] > before[key], key
+
+
+def test_emu_bucket_maxima_paths(emu, oracle):
+    """Bucket-maxima variant: the look-up and the scan fall-back, the "+1" and the 64-bit-max table update
+    must all have run; strengths around the smallest one that has a table (15), the largest, a band that
+    wraps past +-128 (noise), clamped bands (values near 0 and 255) and every colour mode, bit-exact."""
+    before = emu.counters()
+    rng = np.random.default_rng(5)
+    smooth = oracle.synth(48, 16, 5)
+    dark = (rng.integers(0, 30, (10, 33, 4))).astype(np.uint8)            # clamped at 0
+    bright = (255 - rng.integers(0, 30, (10, 33, 4))).astype(np.uint8)    # clamped at 255
+    noise = rng.integers(0, 256, (10, 33, 4), dtype=np.uint8)
+    for s in (14, 15, 16, 20, 31, 63, 127, 128, 255):
+        compare(emu, oracle, [smooth], s, 2, False, BM + 1)
+    for bpp in (1, 2, 3, 4):
+        imgs = [to_bpp(x, bpp) for x in (dark, bright, noise)]
+        compare(emu, oracle, imgs, 20, 2, False, BM + 1)
+        compare(emu, oracle, imgs, 42, 1, True, BM + 2)
+    after = emu.counters()
+    for key in ("bm_lookup", "bm_scan", "bm_fast_update", "bm_general_update"):
         assert after[key] > before[key], key
 
 

@@ -1,11 +1,13 @@
 #!/usr/bin/env python
 """Print the SASS of the K2 pixel loop (from the loop head to the back-edge) for one LPC."""
 import re, subprocess, sys
-lpc = sys.argv[1] if len(sys.argv) > 1 else "8"
+lpc = sys.argv[1] if len(sys.argv) > 1 else "8"   # lanes per channel; append "b" for the bucket-maxima variant (e.g. 1b)
+bm = "1" if lpc.endswith("b") else "0"
+lpc = lpc.rstrip("b")
 lib = [a for a in sys.argv[2:] if a != "-v"][0] if [a for a in sys.argv[2:] if a != "-v"] else "pngloss_b200/libpngloss_b200.so"
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 funcs = out.split("Function : ")
-body = [f for f in funcs if f.startswith(f"_Z14pl_k2_quantizeILi{lpc}E")][0]
+body = [f for f in funcs if f.startswith(f"_Z14pl_k2_quantizeILi{lpc}ELb{bm}E")][0]
 ins = []
 for ln in body.splitlines():
     m = re.match(r"\s+/\*([0-9a-f]{4,5})\*/\s+(.*?);", ln)
