@@ -352,7 +352,7 @@ def main():
                        "strength": a.strength, "bleed": a.bleed,
                        "l2": f"inputs {n * w * h * 4 / 1e9:.1f} GB per GPU >> 126 MB L2, no flush needed",
                        "k2_lanes_per_channel": 8 // info["images_per_cta"],
-                       "k2_candidate_choice": ("bucket maxima" if (a.bm == 1 or (a.bm < 0 and a.strength >= 15))
+                       "k2_candidate_choice": ("bucket maxima" if (a.bm == 1 or (a.bm < 0 and 15 <= a.strength <= 126))
                                                else "scan"),
                        "k2_ctas": info["k2_ctas"], "k2_smem_bytes": info["k2_smem_bytes"],
                        "collective": "nccl all_reduce 256 x u64 per step" if world > 1 else "none (1 GPU)",

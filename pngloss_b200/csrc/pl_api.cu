@@ -400,8 +400,9 @@ extern "C" int pngloss_b200_batch_run(pngloss_b200_batch *b, unsigned strength, 
     PL_CUDA(ctx, cudaGetLastError());
     PL_CUDA(ctx, cudaEventRecord(b->ev[1], b->stream));
     // Bucket maxima replace the per-byte candidate scan by a table look-up; the table only exists for
-    // strength + 1 >= PL_BM_MIN_STEP (at lower strengths the scan is short anyway).
-    const bool bm = ctx->bm >= 0 ? ctx->bm != 0 : strength + 1 >= PL_BM_MIN_STEP;
+    // PL_BM_MIN_STEP <= strength + 1 <= PL_BM_MAX_STEP (below, the scan is short anyway).
+    const bool bm = ctx->bm >= 0 ? ctx->bm != 0
+                                 : (strength + 1 >= PL_BM_MIN_STEP && strength + 1 <= PL_BM_MAX_STEP);
     int rc;
     switch (lpc) {
     case 8: rc = launch_k2<8>(b, nblocks, strength, bleed, bm); break;

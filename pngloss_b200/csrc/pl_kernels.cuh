@@ -174,9 +174,15 @@ struct PlWarpSmem {
 #define PL_DLUT_HALF 512   /* the Sierra tap table covers error values -512 .. 511 (see pl_pack_taps) */
 
 // Bucket-maxima variant (BM): number of entries of PlCtaSmem::bmk per (chain, filter).  Buckets exist
-// for strength + 1 >= 16 (see pl_bm_counts), which gives at most 128/16 + 129/16 = 16 of them.
-#define PL_BM_MAX 16
+// for strength + 1 >= 16 (see pl_bm_counts), which gives at most 128/16 + 1 + 129/16 + 1 = 18 of them.
+#define PL_BM_MAX 18
 #define PL_BM_MIN_STEP 16
+// ... and for strength + 1 <= 127: up to there the buckets of one sign never meet around the 256-bin ring,
+// which is what "a bin has at most two buckets" (pl_bm_counts) rests on.
+#define PL_BM_MAX_STEP 127
+// ... and for images narrower than this (relative counts of a row must fit the 17-bit field)
+#define PL_BM_MAX_WIDTH 16384
+#define PL_BM_COUNT_SHIFT 15
 
 template <int LPC, bool BM = false>
 struct PlCtaSmem {
@@ -280,29 +286,48 @@ __device__ __forceinline__ unsigned pl_key_low(bool exact, int pos) {
 // one of a fixed set of intervals of the symbol axis: [k step, k step + q] for want >= 0 and
 // [-k step - q, -k step] for want < 0 (step = q + 1).  Instead of scanning the q + 1 candidates of every
 // byte, the BM variant keeps, per chain and filter, the candidate key of the current winner of every such
-// interval that lies inside [-128, 127] (a "bucket") and looks it up:
-//   * table index: non-negative buckets 0 .. KP-1, then negative buckets KP .. KP+KN-1;
-//   * symbol 0 ends both zero bands; it is a member of bucket 0 only - bucket KP covers [-q, -1] and a
-//     look-up of the band [-q, 0] adds symbol 0 by hand - so that every symbol has at most one bucket;
-//   * key layout as below, position field relative to the first symbol of the bucket, exact bit clear;
-//   * symbol counts only grow, so "maximum of every key the bucket's symbols ever had" is the current
-//     winner: the table is kept up to date by a 64-bit max (or, when the chosen symbol already is the
-//     winner of its bucket, by adding 1 to the count field);
+// interval ("bucket") that starts inside [-128, 127] and looks it up:
+//   * table index: non-negative buckets k = 0 .. P1-1 at k, negative buckets k = 0 .. N1-1 at P1 + k;
+//   * the last bucket of either sign reaches beyond +-128 and wraps around the 256-bin histogram, as the
+//     scan does, so its far end shares bins with buckets of the other sign (the "seam");
+//   * symbol 0 ends both zero bands; it is a member of bucket 0 only - negative bucket 0 covers [-q, -1]
+//     and a look-up of the band [-q, 0] adds symbol 0 by hand.  So a bin outside the seam has exactly one
+//     bucket, a bin in the seam two;
+//   * a table entry is two 32-bit words: a per-row base count, and the winner's key relative to it,
+//     [31:15] count - base, [14:7] rank of original_frequency (0..255), [6:0] 127 - position in the bucket
+//     - the order of the candidate key below without the "exact" bit.  The base is the winner's count at
+//     the start of the row minus 4 W: a symbol that starts the row further behind cannot win during it
+//     (a row adds at most 4 W to any count), and no count climbs more than 8 W above the base, which is
+//     why a relative count fits 17 bits for W < 16384 (PL_BM_MAX_WIDTH);
+//   * symbol counts only grow, so "maximum of every key the bucket's symbols had during this row" is the
+//     current winner: after every byte the chosen symbol's new key enters its bucket - its two buckets
+//     in the seam - through one native 32-bit shared-memory atomicMax;
 //   * a band clamped to the byte range is a sub-interval of its bucket: if the bucket winner lies
-//     inside, it also wins the sub-interval; if not - or if the band reaches beyond [-128, 127] - the
+//     inside, it also wins the sub-interval; if not - or if the band starts beyond the last bucket - the
 //     byte falls back to the candidate scan.
 struct PlBm {
-    int KP, KN;
+    int P1, N1;           // number of non-negative / negative buckets (0: no table at this strength)
+    int seam_p, seam_n;   // bins >= seam_p also belong to the last negative bucket, bins <= seam_n to the
+                          // last non-negative one
 };
-__device__ __forceinline__ PlBm pl_bm_counts(int step) {
+__device__ __forceinline__ PlBm pl_bm_counts(int step, int width) {
     PlBm b;
-    b.KP = step >= PL_BM_MIN_STEP ? 128 / step : 0;   // (k + 1) step - 1 <= 127
-    b.KN = step >= PL_BM_MIN_STEP ? 129 / step : 0;   // k step + q <= 128
+    const bool on = step >= PL_BM_MIN_STEP && step <= PL_BM_MAX_STEP && width < PL_BM_MAX_WIDTH;
+    const int KP = 128 / step, KN = 129 / step;   // buckets that lie inside [-128, 127] entirely
+    b.P1 = on ? KP + 1 : 0;
+    b.N1 = on ? KN + 1 : 0;
+    b.seam_p = on ? 256 - KN * step - (step - 1) : 999;
+    b.seam_n = on ? KP * step + (step - 1) - 256 : -999;
     return b;
 }
 // first symbol of bucket t
 __device__ __forceinline__ int pl_bm_low(const PlBm &b, int t, int step) {
-    return t < b.KP ? t * step : -(t - b.KP) * step - (step - 1);
+    return t < b.P1 ? t * step : -(t - b.P1) * step - (step - 1);
+}
+
+// table key of a symbol: count relative to the bucket's base, rank, position in the bucket
+__device__ __forceinline__ unsigned pl_bm_key(unsigned rel_count, unsigned rank, int pos) {
+    return (rel_count << PL_BM_COUNT_SHIFT) | (rank << 7) | (unsigned)(127 - pos);
 }
 
 template <int LPC, bool BM>
@@ -359,21 +384,25 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC, BM> &sm
 
     // BM: the histogram of this candidate was just cloned from the previous row's winner (or restored
     // for a retry at another strength) and the tie-break rank differs per filter, so the bucket winners
-    // are rebuilt at the start of every pass; the lanes of a chain share its KP + KN buckets.
-    const PlBm bmc = pl_bm_counts(BM ? step : 0);
+    // are rebuilt at the start of every pass; the lanes of a chain share its buckets.
+    const PlBm bmc = pl_bm_counts(BM ? step : 0, W);
     unsigned long long *bmrow = sm.bmk[BM ? ci : 0][BM ? F : 0];
     if (BM) {
         if (live) {
-            for (int t = gl; t < bmc.KP + bmc.KN; t += C::GROUP) {
+            for (int t = gl; t < bmc.P1 + bmc.N1; t += C::GROUP) {
                 const int lo_t = pl_bm_low(bmc, t, step);
-                const int np = t == bmc.KP ? q : q + 1;   // bucket KP leaves symbol 0 to bucket 0
+                const int np = t == bmc.P1 ? q : q + 1;   // negative bucket 0 leaves symbol 0 to bucket 0
                 unsigned long long best = 0;
                 for (int p = 0; p < np; p++) {
                     const unsigned long long key =
                         pl_hk_load(hkt, (unsigned)(lo_t + p + rot) * 8u) | (unsigned)(511 - p);
                     best = key > best ? key : best;
                 }
-                bmrow[t] = best;
+                const unsigned mcount = (unsigned)(best >> 32);
+                const unsigned base = mcount > 4u * (unsigned)W ? mcount - 4u * (unsigned)W : 0u;
+                bmrow[t] = ((unsigned long long)base << 32) |
+                           pl_bm_key(mcount - base, ((unsigned)best >> PL_KEY_RANK_SHIFT) & 255u,
+                                     511 - (int)((unsigned)best & 511u));
             }
         }
         __syncwarp();
@@ -457,18 +486,21 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC, BM> &sm
 
             // ---- BM: look the band's winner up ----------------------------------------------------
             bool need_scan = true;
-            int tl = 0;                  // bucket of the unclamped band
-            int wsym_l = 0x7fffffff;     // the symbol bucket tl currently holds (none: no such bucket)
-            bool zero_w0 = false;        // symbol 0 currently wins bucket 0
+            int tl = -1;                 // bucket of the unclamped band (-1: beyond the table)
+            unsigned base_l = 0;         // its base count
             if (BM) {
                 const bool neg = want < 0;
-                const bool tvalid = kq < (unsigned)(neg ? bmc.KN : bmc.KP);
-                tl = tvalid ? (int)kq + (neg ? bmc.KP : 0) : 0;
-                unsigned long long wk = *(volatile unsigned long long *)&bmrow[tl];
-                const unsigned w0low = *(volatile unsigned *)&bmrow[0];
-                zero_w0 = bmc.KP > 0 && (w0low & 511u) == 511u;
-                if (tvalid) wsym_l = lo_u + 511 - (int)((unsigned)wk & 511u);
-                if (neg && kq == 0) {   // band [-q, 0]: symbol 0 lives in bucket 0, add it by hand
+                const bool tvalid = kq < (unsigned)(neg ? bmc.N1 : bmc.P1);
+                tl = tvalid ? (int)kq + (neg ? bmc.P1 : 0) : -1;
+                const unsigned long long e = *(volatile unsigned long long *)&bmrow[tvalid ? tl : 0];
+                const unsigned k32 = (unsigned)e;
+                base_l = (unsigned)(e >> 32);
+                // the winner as a candidate key, position field still relative to the bucket (= to lo_u)
+                unsigned long long wk =
+                    ((unsigned long long)(base_l + (k32 >> PL_BM_COUNT_SHIFT)) << 32) |
+                    (((k32 >> 7) & 255u) << PL_KEY_RANK_SHIFT) | ((k32 & 127u) + 384u);
+                // band [-q, 0]: symbol 0 lives in bucket 0, add it by hand (unless the clamp cut it off)
+                if (neg && kq == 0 && (unsigned)(-lo) <= (unsigned)span) {
                     const unsigned long long k0 = pl_hk_load(hkt, (unsigned)rot * 8u) | (unsigned)(511 - q);
                     wk = k0 > wk ? k0 : wk;
                 }
@@ -547,6 +579,7 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC, BM> &sm
             // provisional winner is final (induction over the channel order).  The test needs only
             // provisional values, so its three steps are independent of each other.
             bool conflict = false;
+            unsigned dup = 0;   // BM: earlier channels whose provisional winner is this channel's
             {
                 // one word per channel group: winner's count (saturated to 24 bits, which only makes the
                 // test more conservative) and its symbol
@@ -556,28 +589,16 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC, BM> &sm
                 for (int t2 = 0; t2 < 3; t2++) {
                     const unsigned theirs = __shfl_sync(PL_FULL, mine, ci * C::GROUP + t2 * LPC);
                     const int pos = ((int)(theirs & 255u) - lo) & 255;
-                    conflict |= (ch > t2) & act & (bool)((chmask >> t2) & 1) & (pos <= span) &
-                                (pos != bpos) & ((theirs >> 8) + 3u >= bf);
+                    const bool earlier = (ch > t2) & act & (bool)((chmask >> t2) & 1);
+                    conflict |= earlier & (pos <= span) & (pos != bpos) & ((theirs >> 8) + 3u >= bf);
+                    if (BM) dup += (unsigned)(earlier & (pos == bpos));
                 }
             }
-            // BM: with the provisional winner final, is the bucket table kept current by a plain
-            // "count + 1" (the chosen symbol is the winner its bucket already holds)?
-            bool hit_l = false, bm_slow = false;
-            if (BM) {
-                const int psym = lo + bpos;
-                hit_l = psym == wsym_l;
-                bm_slow = act && !(hit_l || (psym == 0 && zero_w0));
-            }
-            bool general = false;   // BM: the bucket table needs the general (64-bit max) update
-            bool replay;
-            if (!BM) {
-                replay = __any_sync(PL_FULL, conflict);
-            } else {   // one vote on the fast path, a second one only where the first said "slow"
-                general = __any_sync(PL_FULL, conflict || bm_slow);
-                replay = general && __any_sync(PL_FULL, conflict);
-            }
-            if (!replay) {
+            if (!__any_sync(PL_FULL, conflict)) {
                 PL_EMU_COUNT(PL_CNT_FIXUP_SKIPPED);
+                // every provisional winner is final; this channel's symbol has been counted dup times
+                // since the look-up
+                if (BM) bkey += (unsigned long long)dup << 32;
             } else {
                 PL_EMU_COUNT(PL_CNT_FIXUP_REPLAY);
                 // Slow path (rare once counts have spread): the exact sequential replay.
@@ -609,24 +630,33 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC, BM> &sm
             const int back = act ? sym + pred : 0;
             if (act && sub == 0) {
                 unsigned *cnt = (unsigned *)&hk[(unsigned)(sym + rot) & 255u] + 1;   // high word = count
-                if (!BM) {
-                    atomicAdd(cnt, 1u);
-                } else if (!general) {
-                    PL_EMU_COUNT(PL_CNT_BM_FASTUPD);
-                    atomicAdd(cnt, 1u);
-                    atomicAdd((unsigned *)&bmrow[hit_l ? tl : 0] + 1, 1u);
-                } else {
-                    PL_EMU_COUNT(PL_CNT_BM_GENERAL);
-                    // the symbol's new key enters its bucket (if it has one) by a 64-bit maximum
-                    const unsigned now = atomicAdd(cnt, 1u) + 1u;
+                atomicAdd(cnt, 1u);
+                if (BM && bmc.P1 > 0) {
+                    // the symbol's new key enters its bucket - in the seam: its two buckets.  The count
+                    // field of bkey is the symbol's count just before this channel's increment (the replay
+                    // and the dup correction above keep it so).
+                    const unsigned now = (unsigned)(bkey >> 32) + 1u;
+                    const unsigned rank = ((unsigned)bkey >> PL_KEY_RANK_SHIFT) & 255u;
                     const int s8 = (int)(signed char)sym;   // the histogram bin, as a symbol in [-128, 127]
                     const unsigned ks = pl_udiv_magic((unsigned)(s8 < 0 ? -s8 : s8), step_magic);
-                    if (ks < (unsigned)(s8 < 0 ? bmc.KN : bmc.KP)) {
-                        const int ts = (int)ks + (s8 < 0 ? bmc.KP : 0);
-                        const int pos_b = s8 - pl_bm_low(bmc, ts, step);
-                        const unsigned long long nk = ((unsigned long long)now << 32) |
-                                                      ((unsigned)bkey & ~1023u) | (unsigned)(511 - pos_b);
-                        atomicMax(&bmrow[ts], nk);
+                    const int t1 = (int)ks + (s8 < 0 ? bmc.P1 : 0);
+                    unsigned *e1 = (unsigned *)&bmrow[t1];
+                    const unsigned base1 = t1 == tl ? base_l : *(volatile unsigned *)(e1 + 1);
+                    if (now >= base1)
+                        atomicMax(e1, pl_bm_key(now - base1, rank, s8 - pl_bm_low(bmc, t1, step)));
+                    if (s8 >= bmc.seam_p || s8 <= bmc.seam_n) {
+                        PL_EMU_COUNT(PL_CNT_BM_GENERAL);
+                        // bins >= seam_p: also symbol s8 - 256 of the last negative bucket;
+                        // bins <= seam_n: also symbol s8 + 256 of the last non-negative bucket
+                        const bool up = s8 <= bmc.seam_n;
+                        const int t2 = up ? bmc.P1 - 1 : bmc.P1 + bmc.N1 - 1;
+                        unsigned *e2 = (unsigned *)&bmrow[t2];
+                        const unsigned base2 = *(volatile unsigned *)(e2 + 1);
+                        if (now >= base2)
+                            atomicMax(e2, pl_bm_key(now - base2, rank,
+                                                    s8 + (up ? 256 : -256) - pl_bm_low(bmc, t2, step)));
+                    } else {
+                        PL_EMU_COUNT(PL_CNT_BM_FASTUPD);
                     }
                 }
                 ((unsigned char *)&ws.back[ci][i + 1])[ch] = (unsigned char)back;
