@@ -100,16 +100,36 @@ typedef struct {
     uint32_t bytes_per_pixel;   /* out: colour mode used */
     uint32_t retried_rows;      /* out: strength decrements that were needed (normally 0) */
     int status;                 /* out: PNGLOSS_B200_* for this image */
+    unsigned char *out_pixels;  /* NULL: quantise `pixels` in place; else the result goes here and */
+    size_t out_stride;          /* `pixels` is left alone */
 } pngloss_b200_image;
 
 /* Upload, run, download a batch of independent images.  Blocking.  Returns the first non-zero
- * per-image status, or 0. */
+ * per-image status, or 0.  A batch that does not fit the device runs as consecutive groups whose
+ * copies overlap each other's kernels.  The pixels of an image that ends with
+ * PNGLOSS_B200_NO_ACCEPTABLE_ROW are unspecified (the reference abort()s at that point). */
 int pngloss_b200_optimize_batch(pngloss_b200_ctx *ctx, pngloss_b200_image *images, size_t n,
                                 unsigned strength, long bleed);
+
+/* The same, asynchronous: submit enqueues the uploads, kernels and downloads of one batch and returns;
+ * wait blocks until its results are in the host buffers, fills the out fields of `images` and frees the
+ * job.  Several jobs may be in flight: their kernels run one after the other, while the PCIe copies of
+ * one job overlap the kernels of another (use pinned host memory, pngloss_b200_host_alloc, or the copies
+ * are not asynchronous).  `images` and the buffers it points to must stay valid until wait returns.
+ * When the device cannot hold another batch, submit first waits for the oldest job in flight. */
+typedef struct pngloss_b200_job pngloss_b200_job;
+int pngloss_b200_submit(pngloss_b200_ctx *ctx, pngloss_b200_image *images, size_t n, unsigned strength,
+                        long bleed, pngloss_b200_job **job);
+int pngloss_b200_wait(pngloss_b200_job *job);
 
 /* Device-resident batch: allocate once, then upload / run / download as often as wanted. */
 int pngloss_b200_batch_create(pngloss_b200_ctx *ctx, size_t n, const uint32_t *widths,
                               const uint32_t *heights, pngloss_b200_batch **out);
+/* flags: PNGLOSS_B200_BATCH_IN_PLACE - the quantised rows overwrite the uploaded ones on the device
+ * (half the memory; a second run needs a fresh upload, and download_input then returns the result). */
+#define PNGLOSS_B200_BATCH_IN_PLACE 1u
+int pngloss_b200_batch_create_ex(pngloss_b200_ctx *ctx, size_t n, const uint32_t *widths,
+                                 const uint32_t *heights, unsigned flags, pngloss_b200_batch **out);
 void pngloss_b200_batch_destroy(pngloss_b200_batch *b);
 /* adaptive_all / force_bytes_per_pixel per image; defaults 0 / 0 */
 int pngloss_b200_batch_set_mode(pngloss_b200_batch *b, size_t i, int adaptive_all,

@@ -29,7 +29,8 @@ EXPORTS = [
     "pngloss_b200_device_count", "pngloss_b200_ctx_create", "pngloss_b200_ctx_destroy",
     "pngloss_b200_ctx_error", "pngloss_b200_ctx_set_lanes", "pngloss_b200_ctx_set_bucket_maxima", "pngloss_b200_ctx_timer_start",
     "pngloss_b200_ctx_timer_stop", "pngloss_b200_ctx_sync", "pngloss_b200_host_alloc",
-    "pngloss_b200_host_free", "pngloss_b200_optimize_batch", "pngloss_b200_batch_create",
+    "pngloss_b200_host_free", "pngloss_b200_optimize_batch", "pngloss_b200_submit", "pngloss_b200_wait",
+    "pngloss_b200_batch_create", "pngloss_b200_batch_create_ex",
     "pngloss_b200_batch_destroy", "pngloss_b200_batch_set_mode", "pngloss_b200_batch_upload",
     "pngloss_b200_batch_upload_rows", "pngloss_b200_batch_synth", "pngloss_b200_batch_run",
     "pngloss_b200_batch_download", "pngloss_b200_batch_download_rows",
@@ -58,7 +59,7 @@ class ImageDesc(ctypes.Structure):
                 ("width", ctypes.c_uint32), ("height", ctypes.c_uint32),
                 ("row_filters", ctypes.c_void_p), ("force_bytes_per_pixel", ctypes.c_uint32),
                 ("bytes_per_pixel", ctypes.c_uint32), ("retried_rows", ctypes.c_uint32),
-                ("status", ctypes.c_int)]
+                ("status", ctypes.c_int), ("out_pixels", ctypes.c_void_p), ("out_stride", ctypes.c_size_t)]
 
 
 _lib = None
@@ -101,6 +102,10 @@ def load_library() -> ctypes.CDLL:
     L.pngloss_b200_optimize_batch.argtypes = [vp, ctypes.POINTER(ImageDesc), sz, ctypes.c_uint,
                                               ctypes.c_long]
     L.pngloss_b200_batch_create.argtypes = [vp, sz, vp, vp, ctypes.POINTER(vp)]
+    L.pngloss_b200_submit.argtypes = [vp, ctypes.POINTER(ImageDesc), sz, ctypes.c_uint, ctypes.c_long,
+                                      ctypes.POINTER(vp)]
+    L.pngloss_b200_wait.argtypes = [vp]
+    L.pngloss_b200_batch_create_ex.argtypes = [vp, sz, vp, vp, ctypes.c_uint, ctypes.POINTER(vp)]
     L.pngloss_b200_batch_destroy.argtypes = [vp]
     L.pngloss_b200_batch_destroy.restype = None
     L.pngloss_b200_batch_set_mode.argtypes = [vp, sz, i32, u32]
@@ -223,11 +228,8 @@ class Context:
         p, lib = _PINNED.pop(arr.ctypes.data)
         lib.pngloss_b200_host_free(p)
 
-    def optimize_batch(self, images: Sequence[np.ndarray],
-                       row_filters: Optional[Sequence[Optional[np.ndarray]]], strength: int,
-                       bleed: int, force_bpp: int = 0) -> List[dict]:
-        """Host-buffer batch: images are quantised in place.  row_filters: list of (h,) uint8 arrays,
-        entries (or the list) may be None for the reference's row_filters == NULL semantics."""
+    @staticmethod
+    def _descs(images, row_filters, force_bpp, outputs=None):
         n = len(images)
         descs = (ImageDesc * n)()
         for i, a in enumerate(images):
@@ -239,10 +241,34 @@ class Context:
             descs[i].height = a.shape[0]
             descs[i].row_filters = rf.ctypes.data if rf is not None else None
             descs[i].force_bytes_per_pixel = force_bpp
-        rc = self.lib.pngloss_b200_optimize_batch(self.handle, descs, n, strength, bleed)
+            if outputs is not None:
+                o = outputs[i]
+                assert o.dtype == np.uint8 and o.shape == a.shape and o.strides[1] == 4
+                descs[i].out_pixels = o.ctypes.data
+                descs[i].out_stride = o.strides[0]
+        return descs
+
+    def optimize_batch(self, images: Sequence[np.ndarray],
+                       row_filters: Optional[Sequence[Optional[np.ndarray]]], strength: int,
+                       bleed: int, force_bpp: int = 0,
+                       outputs: Optional[Sequence[np.ndarray]] = None) -> List[dict]:
+        """Host-buffer batch: images are quantised in place (or into `outputs`).  row_filters: list of
+        (h,) uint8 arrays, entries (or the list) may be None for the reference's row_filters == NULL
+        semantics."""
+        descs = self._descs(images, row_filters, force_bpp, outputs)
+        rc = self.lib.pngloss_b200_optimize_batch(self.handle, descs, len(images), strength, bleed)
         self._check(rc)
         return [dict(status=d.status, bytes_per_pixel=d.bytes_per_pixel, retried_rows=d.retried_rows)
                 for d in descs]
+
+    def submit(self, images, row_filters, strength: int, bleed: int, force_bpp: int = 0, outputs=None) -> "Job":
+        """Asynchronous optimize_batch (pngloss_b200_submit): returns a Job; Job.wait() blocks and returns
+        the per-image results.  The arrays must stay alive (and untouched) until then."""
+        descs = self._descs(images, row_filters, force_bpp, outputs)
+        handle = ctypes.c_void_p()
+        self._check(self.lib.pngloss_b200_submit(self.handle, descs, len(images), strength, bleed,
+                                                 ctypes.byref(handle)))
+        return Job(self, handle, descs, (images, row_filters, outputs))
 
     def close(self):
         if self.handle:
@@ -256,22 +282,39 @@ class Context:
             pass
 
 
+class Job:
+    """One batch in flight (pngloss_b200_submit / pngloss_b200_wait)."""
+
+    def __init__(self, ctx, handle, descs, keepalive):
+        self.ctx, self.handle, self.descs, self.keepalive = ctx, handle, descs, keepalive
+
+    def wait(self) -> List[dict]:
+        rc = self.ctx.lib.pngloss_b200_wait(self.handle)
+        self.handle = None
+        if rc and rc != NO_ACCEPTABLE_ROW:
+            self.ctx._check(rc)
+        return [dict(status=d.status, bytes_per_pixel=d.bytes_per_pixel, retried_rows=d.retried_rows)
+                for d in self.descs]
+
+
 _PINNED = {}
 
 
 class Batch:
     """Device-resident batch (pngloss_b200_batch_*)."""
 
-    def __init__(self, ctx: Context, widths: Sequence[int], heights: Sequence[int]):
+    def __init__(self, ctx: Context, widths: Sequence[int], heights: Sequence[int], in_place: bool = False):
+        """in_place: the quantised rows overwrite the uploaded ones on the device (half the memory; every
+        run needs a fresh upload and download_input returns the result afterwards)."""
         self.ctx = ctx
         self.lib = ctx.lib
         self.n = len(widths)
         self.widths = np.asarray(widths, np.uint32)
         self.heights = np.asarray(heights, np.uint32)
         self.handle = ctypes.c_void_p()
-        ctx._check(self.lib.pngloss_b200_batch_create(ctx.handle, self.n, self.widths.ctypes.data,
-                                                      self.heights.ctypes.data,
-                                                      ctypes.byref(self.handle)))
+        ctx._check(self.lib.pngloss_b200_batch_create_ex(ctx.handle, self.n, self.widths.ctypes.data,
+                                                         self.heights.ctypes.data, 1 if in_place else 0,
+                                                         ctypes.byref(self.handle)))
 
     def set_mode(self, i, adaptive_all=False, force_bpp=0):
         self.ctx._check(self.lib.pngloss_b200_batch_set_mode(self.handle, i, int(adaptive_all), force_bpp))

@@ -9,12 +9,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 #include <mutex>
 #include <new>
 #include <vector>
 
 #include "pl_kernels.cuh"
 
+struct pngloss_b200_job;
 struct pngloss_b200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -23,7 +25,10 @@ struct pngloss_b200_ctx {
     int lpc = 0;
     int bm = -1;   // bucket-maxima variant of K2: -1 choose from the strength, 0 off, 1 on
     char err[512] = {0};
-    pngloss_b200_batch *cached = nullptr;   // last batch built by pngloss_b200_optimize_batch
+    // job API (pngloss_b200_submit / _wait): copy streams, the device batches it recycles, jobs in flight
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    std::vector<pngloss_b200_batch *> pool;
+    std::vector<pngloss_b200_job *> inflight;   // in submission order
 };
 
 struct pngloss_b200_batch {
@@ -43,11 +48,28 @@ struct pngloss_b200_batch {
     uint32_t *chan_hist = nullptr, *flags = nullptr, *status = nullptr, *final_hist = nullptr;
     unsigned long long *batch_hist = nullptr;
     std::vector<int> hslots;
-    std::vector<uint32_t> hstatus;
+    uint32_t *hstatus = nullptr;         // pinned: [n][4] status words, copied back asynchronously
+    // row filters of all images, contiguous on the device so that the job API fetches them with one copy
+    unsigned char *dfilters = nullptr, *hfilters = nullptr;   // hfilters: pinned staging, allocated on demand
+    std::vector<size_t> filt_off;
+    size_t filt_bytes = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool ran = false;
     uint32_t info[4] = {0, 0, 0, 0};
     bool desc_dirty = true;
+    bool in_place = false;               // PNGLOSS_B200_BATCH_IN_PLACE: out aliases in
+    // job API
+    bool busy = false;
+    cudaEvent_t ev_up = nullptr, ev_done = nullptr, ev_down = nullptr;
+};
+
+struct pngloss_b200_job {
+    pngloss_b200_ctx *ctx = nullptr;
+    pngloss_b200_batch *batch = nullptr;
+    pngloss_b200_image *images = nullptr;
+    size_t n = 0;
+    bool finalized = false;
+    int rc = 0;
 };
 
 static int set_err(pngloss_b200_ctx *ctx, int code, const char *fmt, ...) {
@@ -105,7 +127,11 @@ extern "C" int pngloss_b200_ctx_create(pngloss_b200_ctx **out, int device, void 
 extern "C" void pngloss_b200_ctx_destroy(pngloss_b200_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->cached) pngloss_b200_batch_destroy(ctx->cached);
+    while (!ctx->inflight.empty()) pngloss_b200_wait(ctx->inflight.front());
+    for (pngloss_b200_batch *b : ctx->pool) pngloss_b200_batch_destroy(b);
+    ctx->pool.clear();
+    if (ctx->h2d) cudaStreamDestroy(ctx->h2d);
+    if (ctx->d2h) cudaStreamDestroy(ctx->d2h);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -127,16 +153,32 @@ extern "C" int pngloss_b200_ctx_set_bucket_maxima(pngloss_b200_ctx *ctx, int mod
     return PNGLOSS_B200_SUCCESS;
 }
 
+// The stopwatch events sit on the compute stream; the copy streams of the job API are joined into it
+// first, so that the interval covers everything enqueued on any of the three.
+static int join_copy_streams(pngloss_b200_ctx *ctx, cudaEvent_t scratch) {
+    for (cudaStream_t s : {ctx->h2d, ctx->d2h}) {
+        if (!s) continue;
+        PL_CUDA(ctx, cudaEventRecord(scratch, s));
+        PL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, scratch, 0));
+    }
+    return PNGLOSS_B200_SUCCESS;
+}
+
 extern "C" int pngloss_b200_ctx_timer_start(pngloss_b200_ctx *ctx) {
     if (!ctx) return PNGLOSS_B200_INVALID_ARGUMENT;
     PL_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (int rc = join_copy_streams(ctx, ctx->t0)) return rc;
     PL_CUDA(ctx, cudaEventRecord(ctx->t0, ctx->stream));
+    // later work on the copy streams must not start before the clock does
+    for (cudaStream_t s : {ctx->h2d, ctx->d2h})
+        if (s) PL_CUDA(ctx, cudaStreamWaitEvent(s, ctx->t0, 0));
     return PNGLOSS_B200_SUCCESS;
 }
 
 extern "C" int pngloss_b200_ctx_timer_stop(pngloss_b200_ctx *ctx, float *ms) {
     if (!ctx || !ms) return PNGLOSS_B200_INVALID_ARGUMENT;
     PL_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (int rc = join_copy_streams(ctx, ctx->t1)) return rc;
     PL_CUDA(ctx, cudaEventRecord(ctx->t1, ctx->stream));
     PL_CUDA(ctx, cudaEventSynchronize(ctx->t1));
     PL_CUDA(ctx, cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
@@ -146,7 +188,9 @@ extern "C" int pngloss_b200_ctx_timer_stop(pngloss_b200_ctx *ctx, float *ms) {
 extern "C" int pngloss_b200_ctx_sync(pngloss_b200_ctx *ctx) {
     if (!ctx) return PNGLOSS_B200_INVALID_ARGUMENT;
     PL_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->h2d) PL_CUDA(ctx, cudaStreamSynchronize(ctx->h2d));
     PL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d2h) PL_CUDA(ctx, cudaStreamSynchronize(ctx->d2h));
     return PNGLOSS_B200_SUCCESS;
 }
 
@@ -164,7 +208,14 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 extern "C" int pngloss_b200_batch_create(pngloss_b200_ctx *ctx, size_t n, const uint32_t *widths,
                                          const uint32_t *heights, pngloss_b200_batch **out) {
-    if (!ctx || !out || !n || !widths || !heights) return PNGLOSS_B200_INVALID_ARGUMENT;
+    return pngloss_b200_batch_create_ex(ctx, n, widths, heights, 0u, out);
+}
+
+extern "C" int pngloss_b200_batch_create_ex(pngloss_b200_ctx *ctx, size_t n, const uint32_t *widths,
+                                            const uint32_t *heights, unsigned flags,
+                                            pngloss_b200_batch **out) {
+    if (!ctx || !out || !n || !widths || !heights || (flags & ~PNGLOSS_B200_BATCH_IN_PLACE))
+        return PNGLOSS_B200_INVALID_ARGUMENT;
     *out = nullptr;
     for (size_t i = 0; i < n; i++) {
         // the reference reader caps rowbytes * height at INT_MAX (src/rwpng.c:286-290)
@@ -177,11 +228,17 @@ extern "C" int pngloss_b200_batch_create(pngloss_b200_ctx *ctx, size_t n, const 
     if (!b) return PNGLOSS_B200_OUT_OF_MEMORY;
     b->ctx = ctx;
     b->stream = ctx->stream;
+    b->in_place = (flags & PNGLOSS_B200_BATCH_IN_PLACE) != 0;
     b->n = n;
     b->w.assign(widths, widths + n);
     b->h.assign(heights, heights + n);
     b->himgs.resize(n);
-    b->hstatus.resize(n * 4);
+    if (cudaMallocHost((void **)&b->hstatus, n * 4 * sizeof(uint32_t)) != cudaSuccess) {
+        cudaGetLastError();
+        delete b;
+        return set_err(ctx, PNGLOSS_B200_OUT_OF_MEMORY, "cudaMallocHost(status) failed");
+    }
+    memset(b->hstatus, 0, n * 4 * sizeof(uint32_t));
     b->order.resize(n);
     for (size_t i = 0; i < n; i++) b->order[i] = (int)i;
     std::stable_sort(b->order.begin(), b->order.end(), [&](int a, int c) {
@@ -200,12 +257,21 @@ extern "C" int pngloss_b200_batch_create(pngloss_b200_ctx *ctx, size_t n, const 
     const size_t o_bhist = take(256 * sizeof(unsigned long long), 16);
     const size_t o_zero_end = take(0, 256);
     const size_t o_final = take(n * 256 * sizeof(uint32_t), 256);
-    std::vector<size_t> o_in(n), o_out(n), o_filt(n), o_err(n), o_cand(n);
+    std::vector<size_t> o_in(n), o_out(n), o_filt(n), o_err(n), o_cand(n), o_oprev(n);
+    b->filt_off.resize(n);
     for (size_t i = 0; i < n; i++) {
-        const size_t px = (size_t)widths[i] * heights[i];
-        o_in[i] = take(px * 4, 256);
-        o_out[i] = take(px * 4, 256);
-        o_filt[i] = take(heights[i], 16);
+        b->filt_off[i] = b->filt_bytes;
+        b->filt_bytes += align_up(heights[i], 16);
+    }
+    const size_t o_filters = take(b->filt_bytes, 256);
+    // pixel buffers of consecutive images lie back to back (when their size is a multiple of 256 bytes), so
+    // that a caller whose host images are contiguous too is served by one copy per direction
+    for (size_t i = 0; i < n; i++) o_in[i] = take((size_t)widths[i] * heights[i] * 4, 256);
+    for (size_t i = 0; i < n; i++)
+        o_out[i] = b->in_place ? o_in[i] : take((size_t)widths[i] * heights[i] * 4, 256);
+    for (size_t i = 0; i < n; i++) {
+        o_oprev[i] = take((size_t)widths[i] * 4, 256);
+        o_filt[i] = o_filters + b->filt_off[i];
         o_err[i] = take((size_t)2 * PL_FILTERS * 2 * (widths[i] + PL_ERR_PAD) * sizeof(short4), 256);
         o_cand[i] = take((size_t)PL_FILTERS * widths[i] * 4, 256);
     }
@@ -213,6 +279,7 @@ extern "C" int pngloss_b200_batch_create(pngloss_b200_ctx *ctx, size_t n, const 
     cudaError_t e = cudaMalloc((void **)&b->slab, b->slab_bytes);
     if (e != cudaSuccess) {
         const size_t want = b->slab_bytes;
+        cudaFreeHost(b->hstatus);
         delete b;
         cudaGetLastError();
         return set_err(ctx, PNGLOSS_B200_OUT_OF_MEMORY, "cudaMalloc(%zu bytes) failed: %s", want,
@@ -226,6 +293,7 @@ extern "C" int pngloss_b200_batch_create(pngloss_b200_ctx *ctx, size_t n, const 
     b->flags = (uint32_t *)(b->slab + o_flags);
     b->status = (uint32_t *)(b->slab + o_status);
     b->batch_hist = (unsigned long long *)(b->slab + o_bhist);
+    b->dfilters = b->slab + o_filters;
     b->final_hist = (uint32_t *)(b->slab + o_final);
     for (size_t i = 0; i < n; i++) {
         PlImageDev &d = b->himgs[i];
@@ -237,6 +305,7 @@ extern "C" int pngloss_b200_batch_create(pngloss_b200_ctx *ctx, size_t n, const 
         d.final_hist = b->final_hist + i * 256;
         d.err = (short4 *)(b->slab + o_err[i]);
         d.cand = (uchar4 *)(b->slab + o_cand[i]);
+        d.oprev = (uchar4 *)(b->slab + o_oprev[i]);
         d.status = b->status + i * 4;
         d.width = widths[i];
         d.height = heights[i];
@@ -257,10 +326,14 @@ extern "C" void pngloss_b200_batch_destroy(pngloss_b200_batch *b) {
     if (!b) return;
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->stream);
-    if (b->ctx->cached == b) b->ctx->cached = nullptr;
     for (int k = 0; k < 4; k++)
         if (b->ev[k]) cudaEventDestroy(b->ev[k]);
+    if (b->ev_up) cudaEventDestroy(b->ev_up);
+    if (b->ev_done) cudaEventDestroy(b->ev_done);
+    if (b->ev_down) cudaEventDestroy(b->ev_down);
     if (b->slab) cudaFree(b->slab);
+    if (b->hstatus) cudaFreeHost(b->hstatus);
+    if (b->hfilters) cudaFreeHost(b->hfilters);
     delete b;
 }
 
@@ -273,16 +346,21 @@ extern "C" int pngloss_b200_batch_set_mode(pngloss_b200_batch *b, size_t i, int 
     return PNGLOSS_B200_SUCCESS;
 }
 
-extern "C" int pngloss_b200_batch_upload(pngloss_b200_batch *b, size_t i, const unsigned char *pixels,
-                                         size_t stride) {
+static int upload_on(pngloss_b200_batch *b, size_t i, const unsigned char *pixels, size_t stride,
+                     cudaStream_t stream) {
     if (!b || i >= b->n || !pixels) return PNGLOSS_B200_INVALID_ARGUMENT;
     pngloss_b200_ctx *ctx = b->ctx;
     const size_t rowbytes = (size_t)b->w[i] * 4;
     if (stride < rowbytes) return set_err(ctx, PNGLOSS_B200_INVALID_ARGUMENT, "stride < width*4");
     PL_CUDA(ctx, cudaSetDevice(ctx->device));
     PL_CUDA(ctx, cudaMemcpy2DAsync((void *)b->himgs[i].in, rowbytes, pixels, stride, rowbytes, b->h[i],
-                                   cudaMemcpyHostToDevice, b->stream));
+                                   cudaMemcpyHostToDevice, stream));
     return PNGLOSS_B200_SUCCESS;
+}
+
+extern "C" int pngloss_b200_batch_upload(pngloss_b200_batch *b, size_t i, const unsigned char *pixels,
+                                         size_t stride) {
+    return upload_on(b, i, pixels, stride, b ? b->stream : nullptr);
 }
 
 // rows[] as the reference hands them over: usually equally spaced (src/rwpng.c lays rgba_data out
@@ -360,8 +438,10 @@ static int choose_lpc(const pngloss_b200_batch *b) {
     return 8;
 }
 
-extern "C" int pngloss_b200_batch_run(pngloss_b200_batch *b, unsigned strength, long bleed) {
-    if (!b) return PNGLOSS_B200_INVALID_ARGUMENT;
+// Host-side part of a run: CTA packing, descriptors and the cleared accumulators, enqueued on `stream`
+// (the batch's own stream, or the job API's upload stream).
+static int prepare_run(pngloss_b200_batch *b, unsigned strength, long bleed, cudaStream_t stream, int *lpc_out,
+                       int *nblocks_out) {
     pngloss_b200_ctx *ctx = b->ctx;
     // same ranges as the CLI checks (reference src/pngloss.c:123,128)
     if (strength > 255 || bleed < 1 || bleed > 32767)
@@ -380,16 +460,31 @@ extern "C" int pngloss_b200_batch_run(pngloss_b200_batch *b, unsigned strength, 
         for (size_t s = 0; s < (size_t)cpw; s++) b->hslots.push_back(k + s < e ? b->order[k + s] : -1);
         k = e;
     }
-    const int nblocks = (int)(b->hslots.size() / cpw);
+    *lpc_out = lpc;
+    *nblocks_out = (int)(b->hslots.size() / cpw);
     if (b->desc_dirty) {
         PL_CUDA(ctx, cudaMemcpyAsync(b->dimgs, b->himgs.data(), b->n * sizeof(PlImageDev),
-                                     cudaMemcpyHostToDevice, b->stream));
+                                     cudaMemcpyHostToDevice, stream));
         b->desc_dirty = false;
     }
     PL_CUDA(ctx, cudaMemcpyAsync(b->dslots, b->hslots.data(), b->hslots.size() * sizeof(int),
-                                 cudaMemcpyHostToDevice, b->stream));
-    PL_CUDA(ctx, cudaMemsetAsync(b->zero_begin, 0, b->zero_bytes, b->stream));
+                                 cudaMemcpyHostToDevice, stream));
+    PL_CUDA(ctx, cudaMemsetAsync(b->zero_begin, 0, b->zero_bytes, stream));
+    return PNGLOSS_B200_SUCCESS;
+}
 
+static int launch_run(pngloss_b200_batch *b, unsigned strength, long bleed, int lpc, int nblocks);
+
+extern "C" int pngloss_b200_batch_run(pngloss_b200_batch *b, unsigned strength, long bleed) {
+    if (!b) return PNGLOSS_B200_INVALID_ARGUMENT;
+    int lpc = 0, nblocks = 0;
+    const int rc = prepare_run(b, strength, bleed, b->stream, &lpc, &nblocks);
+    return rc ? rc : launch_run(b, strength, bleed, lpc, nblocks);
+}
+
+// The three kernels of a run on the batch's (compute) stream.
+static int launch_run(pngloss_b200_batch *b, unsigned strength, long bleed, int lpc, int nblocks) {
+    pngloss_b200_ctx *ctx = b->ctx;
     // K1: enough row slices per image to fill the machine, capped by the image height
     uint32_t hmin = b->h[0];
     for (size_t i = 1; i < b->n; i++) hmin = std::min(hmin, b->h[i]);
@@ -401,8 +496,11 @@ extern "C" int pngloss_b200_batch_run(pngloss_b200_batch *b, unsigned strength, 
     PL_CUDA(ctx, cudaEventRecord(b->ev[1], b->stream));
     // Bucket maxima replace the per-byte candidate scan by a table look-up; the table only exists for
     // PL_BM_MIN_STEP <= strength + 1 <= PL_BM_MAX_STEP (below, the scan is short anyway).
+    uint32_t wmax = 0;
+    for (size_t i = 0; i < b->n; i++) wmax = std::max(wmax, b->w[i]);
     const bool bm = ctx->bm >= 0 ? ctx->bm != 0
-                                 : (strength + 1 >= PL_BM_MIN_STEP && strength + 1 <= PL_BM_MAX_STEP);
+                                 : (strength + 1 >= PL_BM_MIN_STEP && strength + 1 <= PL_BM_MAX_STEP &&
+                                    wmax < PL_BM_MAX_WIDTH);
     int rc;
     switch (lpc) {
     case 8: rc = launch_k2<8>(b, nblocks, strength, bleed, bm); break;
@@ -421,8 +519,8 @@ extern "C" int pngloss_b200_batch_run(pngloss_b200_batch *b, unsigned strength, 
     return PNGLOSS_B200_SUCCESS;
 }
 
-extern "C" int pngloss_b200_batch_download(pngloss_b200_batch *b, size_t i, unsigned char *pixels,
-                                           size_t stride, unsigned char *row_filters) {
+static int download_on(pngloss_b200_batch *b, size_t i, unsigned char *pixels, size_t stride,
+                       unsigned char *row_filters, cudaStream_t stream) {
     if (!b || i >= b->n) return PNGLOSS_B200_INVALID_ARGUMENT;
     pngloss_b200_ctx *ctx = b->ctx;
     const size_t rowbytes = (size_t)b->w[i] * 4;
@@ -430,12 +528,17 @@ extern "C" int pngloss_b200_batch_download(pngloss_b200_batch *b, size_t i, unsi
     if (pixels) {
         if (stride < rowbytes) return set_err(ctx, PNGLOSS_B200_INVALID_ARGUMENT, "stride < width*4");
         PL_CUDA(ctx, cudaMemcpy2DAsync(pixels, stride, b->himgs[i].out, rowbytes, rowbytes, b->h[i],
-                                       cudaMemcpyDeviceToHost, b->stream));
+                                       cudaMemcpyDeviceToHost, stream));
     }
     if (row_filters)
         PL_CUDA(ctx, cudaMemcpyAsync(row_filters, b->himgs[i].filters, b->h[i], cudaMemcpyDeviceToHost,
-                                     b->stream));
+                                     stream));
     return PNGLOSS_B200_SUCCESS;
+}
+
+extern "C" int pngloss_b200_batch_download(pngloss_b200_batch *b, size_t i, unsigned char *pixels,
+                                           size_t stride, unsigned char *row_filters) {
+    return download_on(b, i, pixels, stride, row_filters, b ? b->stream : nullptr);
 }
 
 extern "C" int pngloss_b200_batch_download_rows(pngloss_b200_batch *b, size_t i,
@@ -474,7 +577,7 @@ extern "C" int pngloss_b200_batch_finish(pngloss_b200_batch *b, int *status, uin
     pngloss_b200_ctx *ctx = b->ctx;
     PL_CUDA(ctx, cudaSetDevice(ctx->device));
     if (b->ran)
-        PL_CUDA(ctx, cudaMemcpyAsync(b->hstatus.data(), b->status, b->n * 4 * sizeof(uint32_t),
+        PL_CUDA(ctx, cudaMemcpyAsync(b->hstatus, b->status, b->n * 4 * sizeof(uint32_t),
                                      cudaMemcpyDeviceToHost, b->stream));
     PL_CUDA(ctx, cudaStreamSynchronize(b->stream));
     int first = PNGLOSS_B200_SUCCESS;
@@ -535,72 +638,216 @@ extern "C" int pngloss_b200_batch_launch_info(pngloss_b200_batch *b, uint32_t in
     return PNGLOSS_B200_SUCCESS;
 }
 
-// Upper bound of what pngloss_b200_batch_create allocates for one image (see its slab layout).
+// Upper bound of what an in-place batch allocates for one image (see the slab layout in batch_create_ex).
 static size_t device_bytes_per_image(uint32_t w, uint32_t h) {
     const size_t px = (size_t)w * h;
-    return 2 * align_up(px * 4, 256) + align_up(h, 16) +
+    return align_up(px * 4, 256) + align_up((size_t)w * 4, 256) + align_up(h, 16) +
            align_up((size_t)2 * PL_FILTERS * 2 * (w + PL_ERR_PAD) * sizeof(short4), 256) +
            align_up((size_t)PL_FILTERS * w * 4, 256) + PL_FILTERS * 4 * 256 * sizeof(uint32_t) +
            256 * sizeof(uint32_t) + sizeof(PlImageDev) + 8 * sizeof(int) + 64 + 1024;
 }
 
-// ---- host-buffer batch ---------------------------------------------------------------------------------
-// One group of images that fits the device: upload, run, download on the context's stream.
-static int optimize_group(pngloss_b200_ctx *ctx, pngloss_b200_image *images, size_t n, unsigned strength,
-                          long bleed) {
+// ---- host-buffer jobs -----------------------------------------------------------------------------------
+// A job is one batch of host images on its way through the device: uploads on the context's upload
+// stream, the three kernels on its compute stream, downloads on its download stream, chained by events.
+// Kernels of consecutive jobs run back to back on the one compute stream (two K2 grids sharing the SMs
+// was measured and rejected); what overlaps are the PCIe copies of one job with the kernels of
+// another.  Device batches are in-place (the quantised rows overwrite the uploaded ones), so two jobs of
+// the bench's size fit next to each other.
+static int finalize_job(pngloss_b200_job *job) {
+    if (job->finalized) return job->rc;
+    pngloss_b200_ctx *ctx = job->ctx;
+    pngloss_b200_batch *b = job->batch;
+    job->finalized = true;
+    cudaSetDevice(ctx->device);
+    cudaError_t e = cudaEventSynchronize(b->ev_down);
+    int first = 0;
+    if (e != cudaSuccess) {
+        first = set_err(ctx, PNGLOSS_B200_DEVICE_ERROR, "job failed: %s", cudaGetErrorString(e));
+        for (size_t i = 0; i < job->n; i++) job->images[i].status = first;
+    } else {
+        for (size_t i = 0; i < job->n; i++) {
+            const int st = b->hstatus[i * 4 + 0] == PL_ST_OK ? PNGLOSS_B200_SUCCESS : PNGLOSS_B200_NO_ACCEPTABLE_ROW;
+            job->images[i].status = st;
+            job->images[i].bytes_per_pixel = b->hstatus[i * 4 + 1];
+            job->images[i].retried_rows = b->hstatus[i * 4 + 2];
+            if (job->images[i].row_filters)
+                memcpy(job->images[i].row_filters, b->hfilters + b->filt_off[i], b->h[i]);
+            if (st && !first)
+                first = set_err(ctx, st, "image %zu: no acceptable row even at strength 0", i);
+        }
+    }
+    b->busy = false;
+    job->rc = first;
+    return first;
+}
+
+static void trim_pool(pngloss_b200_ctx *ctx, size_t keep) {
+    // drop idle batches (oldest first) until at most `keep` batches remain
+    for (size_t k = 0; k < ctx->pool.size() && ctx->pool.size() > keep;) {
+        if (!ctx->pool[k]->busy) {
+            pngloss_b200_batch_destroy(ctx->pool[k]);
+            ctx->pool.erase(ctx->pool.begin() + (long)k);
+        } else {
+            k++;
+        }
+    }
+}
+
+// An idle in-place batch of exactly these shapes, recycled (a CLI or service feeding equal batches) or new.
+static int acquire_batch(pngloss_b200_ctx *ctx, const std::vector<uint32_t> &w, const std::vector<uint32_t> &h,
+                         pngloss_b200_batch **out) {
+    for (;;) {
+        for (pngloss_b200_batch *b : ctx->pool)
+            if (!b->busy && b->w == w && b->h == h) { *out = b; return 0; }
+        // idle batches of other shapes only hold memory
+        for (size_t k = 0; k < ctx->pool.size();) {
+            if (!ctx->pool[k]->busy) {
+                pngloss_b200_batch_destroy(ctx->pool[k]);
+                ctx->pool.erase(ctx->pool.begin() + (long)k);
+            } else {
+                k++;
+            }
+        }
+        pngloss_b200_batch *b = nullptr;
+        int rc = ctx->pool.size() >= 2 ? PNGLOSS_B200_OUT_OF_MEMORY
+                                       : pngloss_b200_batch_create_ex(ctx, w.size(), w.data(), h.data(),
+                                                                      PNGLOSS_B200_BATCH_IN_PLACE, &b);
+        if (!rc) {
+            if (cudaEventCreateWithFlags(&b->ev_up, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&b->ev_down, cudaEventDisableTiming) != cudaSuccess) {
+                pngloss_b200_batch_destroy(b);
+                return set_err(ctx, PNGLOSS_B200_DEVICE_ERROR, "cudaEventCreate failed");
+            }
+            if (cudaMallocHost((void **)&b->hfilters, b->filt_bytes) != cudaSuccess) {
+                cudaGetLastError();
+                pngloss_b200_batch_destroy(b);
+                return set_err(ctx, PNGLOSS_B200_OUT_OF_MEMORY, "cudaMallocHost(row filters) failed");
+            }
+            ctx->pool.push_back(b);
+            *out = b;
+            return 0;
+        }
+        // no room (or two batches already): let the oldest job in flight finish and take its place
+        if (rc != PNGLOSS_B200_OUT_OF_MEMORY || ctx->inflight.empty()) return rc;
+        pngloss_b200_job *oldest = nullptr;
+        for (pngloss_b200_job *j : ctx->inflight)
+            if (!j->finalized) { oldest = j; break; }
+        if (!oldest) return rc;
+        finalize_job(oldest);
+    }
+}
+
+extern "C" int pngloss_b200_submit(pngloss_b200_ctx *ctx, pngloss_b200_image *images, size_t n,
+                                   unsigned strength, long bleed, pngloss_b200_job **out) {
+    if (!ctx || !images || !n || !out) return PNGLOSS_B200_INVALID_ARGUMENT;
+    *out = nullptr;
+    for (size_t i = 0; i < n; i++)
+        if (!images[i].pixels) return set_err(ctx, PNGLOSS_B200_INVALID_ARGUMENT, "image %zu: NULL pixels", i);
+    PL_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->h2d) PL_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking));
+    if (!ctx->d2h) PL_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking));
     std::vector<uint32_t> w(n), h(n);
     for (size_t i = 0; i < n; i++) {
         w[i] = images[i].width;
         h[i] = images[i].height;
     }
-    // One upload - run - download pass on the context's stream.  Splitting the batch into chunks on
-    // several streams to overlap the PCIe copies with the kernels was measured and rejected: two
-    // co-resident K2 grids do not share the SMs evenly (the older grid's warps win the issue slots, the
-    // younger one finishes 60 % later), which costs more than the ~1.5 s of copies it hides.
-    //
-    // The allocation is reused when the shapes repeat (a CLI or service feeding equal batches).
-    pngloss_b200_batch *b = ctx->cached;
-    if (b && (b->n != n || b->w != w || b->h != h)) {
-        pngloss_b200_batch_destroy(b);
-        b = nullptr;
-    }
-    if (!b) {
-        int rc = pngloss_b200_batch_create(ctx, n, w.data(), h.data(), &b);
-        if (rc) {
-            for (size_t i = 0; i < n; i++) images[i].status = rc;
-            return rc;
+    pngloss_b200_batch *b = nullptr;
+    int rc = acquire_batch(ctx, w, h, &b);
+    if (rc) return rc;
+    pngloss_b200_job *job = new (std::nothrow) pngloss_b200_job();
+    if (!job) return PNGLOSS_B200_OUT_OF_MEMORY;
+    job->ctx = ctx;
+    job->batch = b;
+    job->images = images;
+    job->n = n;
+
+    // upload stream: descriptors and cleared accumulators (small copies from pageable memory, which wait for
+    // what the stream already holds - so they go first), then the pixels
+    int lpc = 0, nblocks = 0;
+    for (size_t i = 0; i < n && !rc; i++)
+        rc = pngloss_b200_batch_set_mode(b, i, images[i].row_filters == nullptr, images[i].force_bytes_per_pixel);
+    if (!rc) rc = prepare_run(b, strength, bleed, ctx->h2d, &lpc, &nblocks);
+    // (images that are contiguous on the host and on the device travel as one copy: thousands of queued
+    // copies would fill the driver's queue and block this call until the kernels have run)
+    for (size_t i = 0; i < n && !rc;) {
+        size_t e2 = i + 1, bytes = (size_t)b->w[i] * b->h[i] * 4;
+        if (images[i].stride == (size_t)b->w[i] * 4) {
+            while (e2 < n && images[e2].stride == (size_t)b->w[e2] * 4 &&
+                   images[e2].pixels == images[i].pixels + bytes &&
+                   (const unsigned char *)b->himgs[e2].in == (const unsigned char *)b->himgs[i].in + bytes) {
+                bytes += (size_t)b->w[e2] * b->h[e2] * 4;
+                e2++;
+            }
         }
-        ctx->cached = b;
+        if (e2 > i + 1) {
+            if (cudaMemcpyAsync((void *)b->himgs[i].in, images[i].pixels, bytes, cudaMemcpyHostToDevice, ctx->h2d) !=
+                cudaSuccess)
+                rc = set_err(ctx, PNGLOSS_B200_DEVICE_ERROR, "upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        } else {
+            rc = upload_on(b, i, images[i].pixels, images[i].stride, ctx->h2d);
+        }
+        i = e2;
     }
-    int rc = 0;
-    for (size_t i = 0; i < n && !rc; i++) {
-        rc = pngloss_b200_batch_set_mode(b, i, images[i].row_filters == nullptr,
-                                         images[i].force_bytes_per_pixel);
-        if (!rc) rc = pngloss_b200_batch_upload(b, i, images[i].pixels, images[i].stride);
+    cudaError_t e = cudaSuccess;
+    if (!rc) e = cudaEventRecord(b->ev_up, ctx->h2d);
+    // compute stream: kernels, then the per-image status words
+    if (!rc && e == cudaSuccess) e = cudaStreamWaitEvent(b->stream, b->ev_up, 0);
+    if (!rc && e == cudaSuccess) rc = launch_run(b, strength, bleed, lpc, nblocks);
+    if (!rc && e == cudaSuccess)
+        e = cudaMemcpyAsync(b->hstatus, b->status, b->n * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                            b->stream);
+    if (!rc && e == cudaSuccess) e = cudaEventRecord(b->ev_done, b->stream);
+    // download stream: pixels (to out_pixels, or back over the input) and row filters
+    if (!rc && e == cudaSuccess) e = cudaStreamWaitEvent(ctx->d2h, b->ev_done, 0);
+    // (a copy into pageable memory would block this call until the kernels are done, so the row filters
+    // travel through a pinned staging buffer and reach the caller's arrays in pngloss_b200_wait)
+    auto dst_of = [&](size_t i) { return images[i].out_pixels ? images[i].out_pixels : images[i].pixels; };
+    auto dstride_of = [&](size_t i) { return images[i].out_pixels ? images[i].out_stride : images[i].stride; };
+    for (size_t i = 0; i < n && !rc && e == cudaSuccess;) {
+        size_t e2 = i + 1, bytes = (size_t)b->w[i] * b->h[i] * 4;
+        if (dstride_of(i) == (size_t)b->w[i] * 4) {
+            while (e2 < n && dstride_of(e2) == (size_t)b->w[e2] * 4 && dst_of(e2) == dst_of(i) + bytes &&
+                   (const unsigned char *)b->himgs[e2].out == (const unsigned char *)b->himgs[i].out + bytes) {
+                bytes += (size_t)b->w[e2] * b->h[e2] * 4;
+                e2++;
+            }
+        }
+        if (e2 > i + 1)
+            e = cudaMemcpyAsync(dst_of(i), b->himgs[i].out, bytes, cudaMemcpyDeviceToHost, ctx->d2h);
+        else
+            rc = download_on(b, i, dst_of(i), dstride_of(i), nullptr, ctx->d2h);
+        i = e2;
     }
-    if (!rc) rc = pngloss_b200_batch_run(b, strength, bleed);
-    std::vector<int> st(n, 0);
-    std::vector<uint32_t> bpp(n, 0), retried(n, 0);
-    if (!rc) {
-        // pixels are only written back for images that succeeded, so a failed image stays untouched
-        // like the reference's out-of-memory path (src/pngloss_image.c:98-125)
-        int frc = pngloss_b200_batch_finish(b, st.data(), bpp.data(), retried.data());
-        if (frc && frc != PNGLOSS_B200_NO_ACCEPTABLE_ROW) rc = frc;
-        for (size_t i = 0; i < n && !rc; i++)
-            if (!st[i])
-                rc = pngloss_b200_batch_download(b, i, images[i].pixels, images[i].stride,
-                                                 images[i].row_filters);
-        if (!rc) rc = pngloss_b200_ctx_sync(ctx);
+    if (!rc && e == cudaSuccess)
+        e = cudaMemcpyAsync(b->hfilters, b->dfilters, b->filt_bytes, cudaMemcpyDeviceToHost, ctx->d2h);
+    if (!rc && e == cudaSuccess) e = cudaEventRecord(b->ev_down, ctx->d2h);
+    if (!rc && e != cudaSuccess)
+        rc = set_err(ctx, PNGLOSS_B200_DEVICE_ERROR, "enqueue failed: %s", cudaGetErrorString(e));
+    if (rc) {
+        // nothing of this job may be left running on a batch we hand back
+        cudaStreamSynchronize(ctx->h2d);
+        cudaStreamSynchronize(b->stream);
+        cudaStreamSynchronize(ctx->d2h);
+        for (size_t i = 0; i < n; i++) images[i].status = rc;
+        delete job;
+        return rc;
     }
-    int first = rc;
-    for (size_t i = 0; i < n; i++) {
-        images[i].status = rc ? rc : st[i];
-        images[i].bytes_per_pixel = bpp[i];
-        images[i].retried_rows = retried[i];
-        if (!first && st[i]) first = st[i];
-    }
-    if (!rc && first) set_err(ctx, first, "at least one image had no acceptable row even at strength 0");
-    return first;
+    b->busy = true;
+    b->ran = true;
+    ctx->inflight.push_back(job);
+    *out = job;
+    return PNGLOSS_B200_SUCCESS;
+}
+
+extern "C" int pngloss_b200_wait(pngloss_b200_job *job) {
+    if (!job) return PNGLOSS_B200_INVALID_ARGUMENT;
+    pngloss_b200_ctx *ctx = job->ctx;
+    const int rc = finalize_job(job);
+    ctx->inflight.erase(std::remove(ctx->inflight.begin(), ctx->inflight.end(), job), ctx->inflight.end());
+    delete job;
+    return rc;
 }
 
 extern "C" int pngloss_b200_optimize_batch(pngloss_b200_ctx *ctx, pngloss_b200_image *images, size_t n,
@@ -611,12 +858,21 @@ extern "C" int pngloss_b200_optimize_batch(pngloss_b200_ctx *ctx, pngloss_b200_i
     PL_CUDA(ctx, cudaSetDevice(ctx->device));
     // A batch larger than the free device memory is processed as consecutive groups that fit (the
     // reference has no such limit: it holds one image at a time, src/pngloss.c:173-205).
-    size_t free_b = 0, total_b = 0;
+    size_t free_b = 0, total_b = 0, pooled = 0;
     PL_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
-    size_t budget = (size_t)(0.92 * (double)(free_b + (ctx->cached ? ctx->cached->slab_bytes : 0)));
+    for (pngloss_b200_batch *b : ctx->pool)
+        if (!b->busy) pooled += b->slab_bytes;
+    size_t budget = (size_t)(0.92 * (double)(free_b + pooled));
     if (const char *e = getenv("PNGLOSS_B200_MEM_BUDGET_MB"))   // tests: force the grouping on small inputs
         budget = std::min(budget, (size_t)strtoull(e, nullptr, 10) << 20);
+    size_t need_all = 0;
+    for (size_t i = 0; i < n; i++) need_all += device_bytes_per_image(images[i].width, images[i].height);
+    // everything at once if it fits; otherwise groups of half the budget, two in flight, so that the
+    // copies of one group hide behind the kernels of the other
+    const bool grouped = need_all > budget;
+    if (grouped) budget /= 2;
     int first = 0;
+    pngloss_b200_job *prev = nullptr;
     for (size_t begin = 0; begin < n;) {
         size_t end = begin, need = 0;
         while (end < n) {
@@ -625,10 +881,25 @@ extern "C" int pngloss_b200_optimize_batch(pngloss_b200_ctx *ctx, pngloss_b200_i
             need += one;
             end++;
         }
-        const int rc = optimize_group(ctx, images + begin, end - begin, strength, bleed);
-        if (rc && !first) first = rc;
+        pngloss_b200_job *job = nullptr;
+        int rc = pngloss_b200_submit(ctx, images + begin, end - begin, strength, bleed, &job);
+        if (prev) {
+            const int prc = pngloss_b200_wait(prev);
+            if (prc && !first) first = prc;
+            prev = nullptr;
+        }
+        if (rc) {
+            if (!first) first = rc;
+        } else {
+            prev = job;
+        }
         begin = end;
     }
+    if (prev) {
+        const int prc = pngloss_b200_wait(prev);
+        if (prc && !first) first = prc;
+    }
+    if (!grouped) trim_pool(ctx, 1);   // keep one allocation for a caller that repeats the batch
     return first;
 }
 

@@ -253,6 +253,7 @@ __device__ __forceinline__ int pl_image_mode(const PlImageDev &im) {
 struct PlChain {
     const uchar4 *in;
     const uchar4 *out;
+    const uchar4 *oprev;
     short4 *err;
     uchar4 *cand;
     int chmask;       // active RGBA channels: 0x2 gray, 0xA gray+alpha, 0x7 rgb, 0xF rgba
@@ -361,7 +362,7 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC, BM> &sm
     short4 *En0 = cn.err + ((size_t)((parity ^ 1) * PL_FILTERS + F) * 2 + 0) * EW;
     short4 *En1 = En0 + EW;
     const uchar4 *rin = cn.in + (size_t)y * W;
-    const uchar4 *rin_up = cn.in + (size_t)(y ? y - 1 : 0) * W;
+    const uchar4 *rin_up = cn.oprev;   // original row y-1, saved by the commit of row y-1
     const uchar4 *rout_up = cn.out + (size_t)(y ? y - 1 : 0) * W;
     uchar4 *rcand = cn.cand + (size_t)F * W;
 
@@ -802,6 +803,48 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC, BM> &sm
     return cost;
 }
 
+// Row commit: the winner's candidate row becomes row y of the output (which may be the original row
+// itself, in-place batch) and the original row y is kept in the image's scratch row for the predictions of
+// row y + 1.  The compiler must assume that the stores alias the next loads, so every round of this loop
+// costs a full memory latency: four pixels per thread and round where the row allows it.
+#ifndef PL_COMMIT_MODE
+#define PL_COMMIT_MODE 1
+#endif
+#ifdef PL_COMMIT_NOINLINE
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+void pl_commit_row(const PlImageDev &im, int w2, int y, int W, int tid) {
+    const int mode2 = pl_image_mode(im);
+    const bool notgray = mode2 >= 3, notopaque = (mode2 & 1) == 0;
+    const uchar4 *src = im.cand + (size_t)w2 * W;
+    const uchar4 *orig = im.in + (size_t)y * W;
+    uchar4 *dst = im.out + (size_t)y * W;
+    // gray modes: G over R and B (reference src/pngloss_image.c:130-139); opaque modes: alpha 255 (:134,:144)
+    const unsigned sel = notgray ? 0x3210u : 0x3111u, amask = notopaque ? 0u : 0xff000000u;
+    if (PL_COMMIT_MODE == 1 && (W & 3) == 0) {   // rows are 16-byte aligned then (256-byte aligned buffers)
+        const uint4 *src4 = (const uint4 *)src, *orig4 = (const uint4 *)orig;
+        uint4 *dst4 = (uint4 *)dst, *oprev4 = (uint4 *)im.oprev;
+        for (int x = tid; x < W / 4; x += PL_K2_THREADS) {
+            uint4 p = src4[x];
+            const uint4 o = orig4[x];
+            p.x = __byte_perm(p.x, 0u, sel) | amask;
+            p.y = __byte_perm(p.y, 0u, sel) | amask;
+            p.z = __byte_perm(p.z, 0u, sel) | amask;
+            p.w = __byte_perm(p.w, 0u, sel) | amask;
+            oprev4[x] = o;
+            dst4[x] = p;
+        }
+    } else {
+        for (int x = tid; x < W; x += PL_K2_THREADS) {
+            const unsigned p = __byte_perm(pl_u32(src[x]), 0u, sel) | amask;
+            im.oprev[x] = orig[x];
+            dst[x] = pl_uc4(p);
+        }
+    }
+}
+
 template <int LPC, bool BM>
 __global__ void __launch_bounds__(PL_K2_THREADS, PL_K2_MIN_BLOCKS(LPC))
 pl_k2_quantize(const PlImageDev *imgs, const int *slots, int strength, int bleed) {
@@ -834,6 +877,7 @@ pl_k2_quantize(const PlImageDev *imgs, const int *slots, int strength, int bleed
         const int mode = pl_image_mode(im);
         cn.in = im.in;
         cn.out = im.out;
+        cn.oprev = im.oprev;
         cn.err = im.err;
         cn.cand = im.cand;
         cn.gray = mode <= 2;
@@ -947,16 +991,7 @@ pl_k2_quantize(const PlImageDev *imgs, const int *slots, int strength, int bleed
                 if (w2 == -2) continue;
                 if (w2 >= 0) {
                     const PlImageDev &im = sm.img[c2];
-                    const int mode2 = pl_image_mode(im);
-                    const bool notgray = mode2 >= 3, notopaque = (mode2 & 1) == 0;
-                    const uchar4 *src = im.cand + (size_t)w2 * W;
-                    uchar4 *dst = im.out + (size_t)y * W;
-                    for (int x = tid; x < W; x += PL_K2_THREADS) {
-                        uchar4 p = src[x];
-                        if (!notgray) { p.x = p.y; p.z = p.y; }   // widen gray (pngloss_image.c:130-139)
-                        if (!notopaque) p.w = 255;               // strip alpha (:134,:144)
-                        dst[x] = p;
-                    }
+                    pl_commit_row(im, w2, y, W, tid);
                     for (int s = tid; s < 256; s += PL_K2_THREADS) {
                         const unsigned v = (unsigned)(sm.hk[c2][w2 * 256 + s] >> 32);
                         sm.base[c2][s] = v;

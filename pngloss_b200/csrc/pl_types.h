@@ -15,8 +15,11 @@
 // every colour mode; the narrowed 1/2/3 byte-per-pixel modes of the reference are run on the same
 // layout through a channel mask (DESIGN.md "Data layout").
 struct PlImageDev {
-    const uchar4 *in;        // original image, never written
-    uchar4 *out;             // quantised image, row y written once the winner of row y is known
+    const uchar4 *in;        // original image
+    uchar4 *out;             // quantised image, row y written once the winner of row y is known; may be
+                             // the same buffer as `in` (in-place batch): the kernel never reads an
+                             // original row again after its winner is committed
+    uchar4 *oprev;           // scratch [width]: the original row above the row in flight
     unsigned char *filters;  // height libpng filter masks (0x08..0x80)
     uint32_t *chan_hist;     // [5][4][256] per-channel original-image histograms (K1 output)
     uint32_t *flags;         // [0] != 0: some pixel is not gray; [1] != 0: some pixel is not opaque

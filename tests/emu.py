@@ -25,7 +25,8 @@ class Emu:
 
     def optimize(self, imgs, strength, bleed, adaptive_all, lpc):
         """imgs: list of equally sized (h, w, 4) uint8 arrays -> dict of outputs.
-        lpc: lanes per channel (8, 4, 2, 1), + 16 selects the bucket-maxima variant of K2."""
+        lpc: lanes per channel (8, 4, 2, 1), + 16 selects the bucket-maxima variant of K2, + 32 an
+        in-place batch (output buffer = input buffer)."""
         n = len(imgs)
         h, w, _ = imgs[0].shape
         buf = np.ascontiguousarray(np.stack(imgs)).copy()

@@ -20,26 +20,32 @@ extern "C" int emu_optimize(unsigned char *rgba, int n, uint32_t w, uint32_t h,
                             unsigned char *filters_out, int strength, int bleed, int adaptive_all,
                             int lpc, uint32_t *final_hist, uint32_t *status,
                             unsigned long long *batch_hist, uint32_t *chan_hist_out) {
+    // lpc: lanes per channel (8, 4, 2, 1), + 16 for the bucket-maxima variant of K2, + 32 for an
+    // in-place batch (the output buffer is the input buffer)
+    const bool bm = (lpc & 16) != 0, in_place = (lpc & 32) != 0;
+    lpc &= 15;
     const size_t npx = (size_t)w * h;
     const size_t ew = (size_t)w + PL_ERR_PAD;
     std::vector<uchar4> out(npx * n);
     std::vector<uint32_t> chan(5 * 4 * 256 * (size_t)n, 0), flags(2 * (size_t)n, 0);
     std::vector<short4> err(2 * 5 * 2 * ew * n);
-    std::vector<uchar4> cand(5 * (size_t)w * n);
+    std::vector<uchar4> cand(5 * (size_t)w * n), oprev((size_t)w * n);
     memset(err.data(), 0x5A, err.size() * sizeof(short4));   // poison: kernel must not rely on zeros
     memset(cand.data(), 0x5A, cand.size() * sizeof(uchar4));
     memset(out.data(), 0x5A, out.size() * sizeof(uchar4));
+    memset(oprev.data(), 0x5A, oprev.size() * sizeof(uchar4));
     std::vector<PlImageDev> imgs(n);
     for (int i = 0; i < n; i++) {
         PlImageDev &d = imgs[i];
         d.in = (const uchar4 *)rgba + npx * i;
-        d.out = out.data() + npx * i;
+        d.out = in_place ? (uchar4 *)rgba + npx * i : out.data() + npx * i;
         d.filters = filters_out + (size_t)h * i;
         d.chan_hist = chan.data() + 5 * 4 * 256 * (size_t)i;
         d.flags = flags.data() + 2 * (size_t)i;
         d.final_hist = final_hist + 256 * (size_t)i;
         d.err = err.data() + 2 * 5 * 2 * ew * i;
         d.cand = cand.data() + 5 * (size_t)w * i;
+        d.oprev = oprev.data() + (size_t)w * i;
         d.status = status + 3 * (size_t)i;
         d.width = w;
         d.height = h;
@@ -51,9 +57,6 @@ extern "C" int emu_optimize(unsigned char *rgba, int n, uint32_t w, uint32_t h,
     simt::launch([&] { pl_k1_orig_hist(dimgs, k1_slices); }, dim3(k1_slices * n), dim3(PL_K1_THREADS), 0);
     if (chan_hist_out) memcpy(chan_hist_out, chan.data(), chan.size() * sizeof(uint32_t));
 
-    // lpc: lanes per channel (8, 4, 2, 1), + 16 for the bucket-maxima variant of K2
-    const bool bm = (lpc & 16) != 0;
-    lpc &= 15;
     const int cpw = 8 / lpc;
     const int nblocks = (n + cpw - 1) / cpw;
     std::vector<int> slots((size_t)nblocks * cpw, -1);
@@ -69,7 +72,7 @@ extern "C" int emu_optimize(unsigned char *rgba, int n, uint32_t w, uint32_t h,
         memset(batch_hist, 0, 256 * sizeof(unsigned long long));
         simt::launch([&] { pl_k3_batch_hist(dimgs, n, batch_hist); }, dim3(2), dim3(256), 0);
     }
-    memcpy(rgba, out.data(), npx * n * sizeof(uchar4));
+    if (!in_place) memcpy(rgba, out.data(), npx * n * sizeof(uchar4));
     return 0;
 }
 

@@ -378,3 +378,65 @@ def test_invalid_arguments(ctx):
         ctx.optimize_batch([img], None, 20, 0)
     with pytest.raises(pngloss_b200.PnglossError):
         pngloss_b200.Batch(ctx, [0], [4])
+
+
+
+def test_in_place_device_batch(ctx, oracle):
+    """PNGLOSS_B200_BATCH_IN_PLACE: the kernel overwrites the uploaded rows (it keeps the one original row
+    it still needs in a scratch row); results must not change."""
+    imgs = [to_bpp(oracle.synth(97, 33, 50 + i), (i % 4) + 1) for i in range(12)]
+    for lanes, bm in ((8, 0), (2, 1), (1, 1)):
+        ctx.set_lanes(lanes)
+        ctx.set_bucket_maxima(bm)
+        batch = pngloss_b200.Batch(ctx, [97] * 12, [33] * 12, in_place=True)
+        for i, im in enumerate(imgs):
+            batch.upload(i, im)
+        batch.run(20, 2)
+        st, _, _ = batch.finish()
+        assert (st == 0).all()
+        for i, im in enumerate(imgs):
+            want_px, want_rf = oracle.optimize(im, 20, 2, True)
+            out, again = np.zeros_like(im), np.zeros_like(im)
+            rf = np.zeros(33, np.uint8)
+            batch.download(i, out, rf)
+            batch.download_input(i, again)
+            ctx.sync()
+            assert np.array_equal(out, want_px) and np.array_equal(rf, want_rf), (lanes, bm, i)
+            assert np.array_equal(again, want_px)
+        batch.close()
+    ctx.set_lanes(0)
+    ctx.set_bucket_maxima(-1)
+
+
+def test_jobs_in_flight_with_separate_outputs(ctx, oracle):
+    """pngloss_b200_submit / _wait: three jobs in flight (more than the two device batches the library
+    keeps), results into separate output buffers, inputs untouched, waited out of order."""
+    rng = np.random.default_rng(99)
+    jobs = []
+    for j in range(3):
+        imgs = []
+        for i in range(10):
+            im = oracle.synth(120, 40, 700 + 10 * j + i) if i % 2 == 0 else \
+                rng.integers(0, 256, (40, 120, 4), dtype=np.uint8)
+            imgs.append(to_bpp(im, (i % 4) + 1))
+        pinned_in = ctx.pinned_empty((10, 40, 120, 4))
+        pinned_out = ctx.pinned_empty((10, 40, 120, 4))
+        for i, im in enumerate(imgs):
+            pinned_in[i] = im
+        rfs = [np.zeros(40, np.uint8) if i % 3 else None for i in range(10)]
+        job = ctx.submit([pinned_in[i] for i in range(10)], rfs, 20 + j, 2,
+                         outputs=[pinned_out[i] for i in range(10)])
+        jobs.append((job, imgs, pinned_in, pinned_out, rfs, 20 + j))
+    for k in (1, 0, 2):
+        job, imgs, pinned_in, pinned_out, rfs, s = jobs[k]
+        res = job.wait()
+        for i, im in enumerate(imgs):
+            want_px, want_rf = oracle.optimize(im, s, 2, rfs[i] is not None)
+            assert res[i]["status"] == 0
+            assert np.array_equal(pinned_in[i], im), "input buffer was modified"
+            assert np.array_equal(pinned_out[i], want_px), (k, i)
+            if rfs[i] is not None:
+                assert np.array_equal(rfs[i], want_rf), (k, i)
+    for _, _, a, b, _, _ in jobs:
+        ctx.free_pinned(a)
+        ctx.free_pinned(b)

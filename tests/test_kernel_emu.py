@@ -53,7 +53,8 @@ CASES = [  # w, h, seed, bpp, strength, bleed, null_filters
 ]
 
 
-BM = 16   # added to lpc: the bucket-maxima variant of K2 (see emu.py)
+BM = 16        # added to lpc: the bucket-maxima variant of K2 (see emu.py)
+IN_PLACE = 32  # added to lpc: the kernel writes its output over its input
 
 
 @pytest.mark.parametrize("lpc", [8, 4, 2, 1, BM + 8, BM + 2, BM + 1])
@@ -65,14 +66,14 @@ def test_emu_single_image(emu, oracle, case, lpc):
     assert got["status"][0][1] == bpp or (w * h == 1)
 
 
-@pytest.mark.parametrize("lpc", [8, 4, 2, 1, BM + 4, BM + 1])
+@pytest.mark.parametrize("lpc", [8, 4, 2, 1, BM + 4, BM + 1, IN_PLACE + 8, IN_PLACE + BM + 1])
 def test_emu_batch_mixed_modes(emu, oracle, lpc):
     """Several images per CTA (CPW = 8/lpc), every bytes-per-pixel mode, partially filled last CTA."""
     imgs = [to_bpp(oracle.synth(29, 6, 100 + i), (i % 4) + 1) for i in range(11)]
     compare(emu, oracle, imgs, 20, 2, False, lpc)
 
 
-@pytest.mark.parametrize("lpc", [8, 2, 1, BM + 2, BM + 1])
+@pytest.mark.parametrize("lpc", [8, 2, 1, BM + 2, BM + 1, IN_PLACE + BM + 1])
 def test_emu_retry_path(emu, oracle, lpc):
     """row_filters == NULL on tiny noisy images makes the libpng-heuristic check reject all five
     candidates now and then, which exercises the lower-strength retry (reference
