@@ -41,7 +41,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--images", type=int, default=1184, help="images per GPU per step")
+    ap.add_argument("--images", type=int, default=2368,
+                    help="images per GPU per step (default: 16 per SM, two CTAs of 8 images; falls back to "
+                         "half if the device cannot hold them)")
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--strength", type=int, default=20)
@@ -226,8 +228,26 @@ def main():
     n, w, h = a.images, a.width, a.height
     px_per_step_rank = n * w * h
 
+    # the device-resident run keeps inputs and outputs apart (every step re-reads the same inputs):
+    # 2 x 33 MB per 4K image; fall back to half the images where that does not fit
+    while True:
+        try:
+            batch = pngloss_b200.Batch(ctx, [w] * n, [h] * n)
+            break
+        except pngloss_b200.PnglossError as e:
+            if e.code != pngloss_b200.OUT_OF_MEMORY or n <= 8:
+                raise
+            n //= 2
+    if world > 1:                               # same batch on every rank
+        nmin = torch.tensor([n], device=f"cuda:{local_rank}")
+        dist.all_reduce(nmin, op=dist.ReduceOp.MIN)
+        if int(nmin.item()) != n:
+            batch.close()
+            n = int(nmin.item())
+            batch = pngloss_b200.Batch(ctx, [w] * n, [h] * n)
+    a.images = n
+    px_per_step_rank = n * w * h
     seeds = shard_seeds(rank, world, n)        # distinct images on every rank (shards, not replicas)
-    batch = pngloss_b200.Batch(ctx, [w] * n, [h] * n)
     for i in range(n):
         batch.synth(i, seeds[i])
     ctx.sync()
@@ -300,14 +320,19 @@ def main():
         n2 = n
         try:
             avail = int([ln for ln in open("/proc/meminfo") if ln.startswith("MemAvailable")][0].split()[1]) * 1024
-            n2 = max(1, min(n, int(0.6 * avail / world / (3 * img_bytes))))
+            n2 = max(1, min(n, int(0.6 * avail / world / (2 * img_bytes))))
         except Exception:
             pass
-        # One pinned input buffer that no step modifies and two pinned output buffers used in turn: the
-        # steps go through the asynchronous call (pngloss_b200_submit / _wait), two in flight, so that the
-        # upload of step k+1 and the download of step k-1 run under the kernels of step k.
+        if world > 1:
+            nmin = torch.tensor([n2], device=f"cuda:{local_rank}")
+            dist.all_reduce(nmin, op=dist.ReduceOp.MIN)
+            n2 = int(nmin.item())
+        # One pinned input buffer that no step modifies and one pinned output buffer: the steps go through
+        # the asynchronous call (pngloss_b200_submit / _wait), two in flight, so that the upload of step
+        # k+1 and the download of step k-1 run under the kernels of step k.  (A step's results are complete
+        # when its wait returns; the next step's download overwrites them afterwards.)
         src = ctx.pinned_empty((n2, h, w, 4))
-        dst = [ctx.pinned_empty((n2, h, w, 4)) for _ in range(2)]
+        dst = [ctx.pinned_empty((n2, h, w, 4))] * 2
         b2 = pngloss_b200.Batch(ctx, [w] * n2, [h] * n2, in_place=True)
         for i in range(n2):
             b2.synth(i, seeds[i])
@@ -347,10 +372,8 @@ def main():
                "ms_per_step": e_step, "wall_ms_per_step": e_wall / a.steps, "images_per_gpu": n2,
                "api": "pngloss_b200_submit / pngloss_b200_wait, two steps in flight (pinned host input and "
                       "output buffers; every step uploads its input and downloads its result)"}
-        # the result of the last step must be the same as what the device-resident run produced
         ctx.free_pinned(src)
-        for d in dst:
-            ctx.free_pinned(d)
+        ctx.free_pinned(dst[0])
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -366,8 +389,7 @@ def main():
                        "strength": a.strength, "bleed": a.bleed,
                        "l2": f"inputs {n * w * h * 4 / 1e9:.1f} GB per GPU >> 126 MB L2, no flush needed",
                        "k2_lanes_per_channel": 8 // info["images_per_cta"],
-                       "k2_candidate_choice": ("bucket maxima" if (a.bm == 1 or (a.bm < 0 and 15 <= a.strength <= 126))
-                                               else "scan"),
+                       "k2_candidate_choice": "bucket maxima" if info["bucket_maxima"] else "scan",
                        "k2_ctas": info["k2_ctas"], "k2_smem_bytes": info["k2_smem_bytes"],
                        "collective": "nccl all_reduce 256 x u64 per step" if world > 1 else "none (1 GPU)",
                        "wall_ms_per_step": wall_ms / a.steps},

@@ -157,7 +157,7 @@ void *pngloss_b200_batch_histogram_device(pngloss_b200_batch *b);
  * [2] batch-histogram kernel, [3] whole run.  Valid after finish. */
 int pngloss_b200_batch_timings(pngloss_b200_batch *b, float ms[4]);
 /* Launch geometry of the last run: [0] quantise CTAs, [1] images per CTA, [2] dynamic smem bytes,
- * [3] kernels launched. */
+ * [3] kernels launched (bits 0-7) and, bit 8, whether the quantise kernel used the bucket-maxima table. */
 int pngloss_b200_batch_launch_info(pngloss_b200_batch *b, uint32_t info[4]);
 
 #ifdef __cplusplus

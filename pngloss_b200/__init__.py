@@ -371,7 +371,8 @@ class Batch:
     def launch_info(self):
         info = (ctypes.c_uint32 * 4)()
         self.ctx._check(self.lib.pngloss_b200_batch_launch_info(self.handle, info))
-        return dict(k2_ctas=info[0], images_per_cta=info[1], k2_smem_bytes=info[2], launches=info[3])
+        return dict(k2_ctas=info[0], images_per_cta=info[1], k2_smem_bytes=info[2], launches=info[3] & 0xff,
+                    bucket_maxima=bool(info[3] & 0x100))
 
     def close(self):
         if self.handle:

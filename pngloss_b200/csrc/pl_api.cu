@@ -498,9 +498,11 @@ static int launch_run(pngloss_b200_batch *b, unsigned strength, long bleed, int 
     // PL_BM_MIN_STEP <= strength + 1 <= PL_BM_MAX_STEP (below, the scan is short anyway).
     uint32_t wmax = 0;
     for (size_t i = 0; i < b->n; i++) wmax = std::max(wmax, b->w[i]);
+    // ... and it only pays where a lane scans many candidates itself (one or two lanes per channel; measured,
+    // profiles/r1_sweep_lanes_bm.txt)
     const bool bm = ctx->bm >= 0 ? ctx->bm != 0
                                  : (strength + 1 >= PL_BM_MIN_STEP && strength + 1 <= PL_BM_MAX_STEP &&
-                                    wmax < PL_BM_MAX_WIDTH);
+                                    wmax < PL_BM_MAX_WIDTH && lpc <= 2);
     int rc;
     switch (lpc) {
     case 8: rc = launch_k2<8>(b, nblocks, strength, bleed, bm); break;
@@ -514,7 +516,7 @@ static int launch_run(pngloss_b200_batch *b, unsigned strength, long bleed, int 
                                                                                     b->batch_hist);
     PL_CUDA(ctx, cudaGetLastError());
     PL_CUDA(ctx, cudaEventRecord(b->ev[3], b->stream));
-    b->info[3] = 3;
+    b->info[3] = 3 | (bm ? 0x100u : 0u);
     b->ran = true;
     return PNGLOSS_B200_SUCCESS;
 }
