@@ -481,15 +481,48 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC, BM> &sm
             }
             const int span = act ? hi - lo : -1;
 
-            unsigned long long acc[C::NACC];
+            // ---- candidate scan against the histogram at the start of the pixel ---------------
+            // Every lane looks at candidates sub, sub + LPC, ...; the trip count comes from the
+            // strength (warp-uniform), candidates beyond the clamped band are predicated off, and the
+            // body is unrolled so that the independent shared-memory loads are in flight together.
+            // NACC running maxima (merged after the scan) keep the compare chain short where a lane looks
+            // at many candidates.
+            auto scan = [&](unsigned long long(&acc)[C::NACC]) {
+                const int jl = (span - sub) >> C::LOG2LPC;          // last valid j of this lane (-1: none)
+                const unsigned off0 = (unsigned)(lo + sub + rot) * 8u;   // byte offset of candidate j = 0
+                const unsigned low0 = 511u - (unsigned)sub;          // its "511 - pos" field
+                const int jx = ex - lo - sub;                        // j * LPC of the exact symbol, if mine
+                // (BM: only this lane's own candidates - the scan runs diverged there anyway and a clamped
+                // band is usually short)
+                for (int j0 = 0; j0 < (BM ? jl + 1 : jmax); j0 += C::UNR) {
+                    // per-chunk bases, so that each candidate below only adds compile-time constants
+                    const unsigned off_c = off0 + (unsigned)(j0 * LPC * 8);
+                    const unsigned low_c = low0 - (unsigned)(j0 * LPC);
+                    const int jl_c = jl - j0, jx_c = jx - j0 * LPC;
 #pragma unroll
-            for (int k = 0; k < C::NACC; k++) acc[k] = 0;
+                    for (int u = 0; u < C::UNR; u++) {
+                        unsigned long long key = pl_hk_load(hkt, off_c + (unsigned)(u * LPC * 8));
+                        key |= low_c - (unsigned)(u * LPC);          // low 10 bits of an entry are zero
+                        if (!C::EXSEP) key |= (unsigned)(u * LPC == jx_c) << 9;
+                        unsigned long long &a = acc[u % C::NACC];
+                        a = (u <= jl_c && key > a) ? key : a;
+                    }
+                }
+            };
+            // the exact symbol as a candidate of its own, with its bonus bit; every lane of the group may
+            // add it (max is idempotent)
+            auto exact_candidate = [&](unsigned long long &a) {
+                const int pos = ex - lo;
+                const unsigned long long key =
+                    pl_hk_load(hkt, (unsigned)(ex + rot) * 8u) | pl_key_low(true, pos & 255);
+                a = (pos >= 0 && pos <= span && key > a) ? key : a;
+            };
 
-            // ---- BM: look the band's winner up ----------------------------------------------------
-            bool need_scan = true;
-            int tl = -1;                 // bucket of the unclamped band (-1: beyond the table)
-            unsigned base_l = 0;         // its base count
+            unsigned long long acc0;
+            int tl = -1;                 // BM: bucket of the unclamped band (-1: beyond the table)
+            unsigned base_l = 0;         // BM: its base count
             if (BM) {
+                // ---- look the band's winner up ------------------------------------------------------
                 const bool neg = want < 0;
                 const bool tvalid = kq < (unsigned)(neg ? bmc.N1 : bmc.P1);
                 tl = tvalid ? (int)kq + (neg ? bmc.P1 : 0) : -1;
@@ -508,59 +541,41 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC, BM> &sm
                 const int wsym = lo_u + 511 - (int)((unsigned)wk & 511u);
                 const bool inr = tvalid && wsym >= lo && wsym <= hi;
                 // position field relative to the clamped band: 511 - (wsym - lo)
-                if (act && inr) acc[0] = wk + (unsigned long long)(unsigned)(lo - lo_u);
+                acc0 = act && inr ? wk + (unsigned long long)(unsigned)(lo - lo_u) : 0ull;
                 // a band of one symbol that is the exact symbol is covered by the exact candidate below
-                need_scan = act && !inr && !(span == 0 && ex == lo);
+                const bool need_scan = act && !inr && !(span == 0 && ex == lo);
 #ifdef PL_SIMT_EMU
                 // path statistics, per warp iteration: does any lane of the warp scan?
                 if (__any_sync(PL_FULL, need_scan)) PL_EMU_COUNT(PL_CNT_BM_SCAN);
                 else PL_EMU_COUNT(PL_CNT_BM_LOOKUP);
 #endif
-            }
-
-            // ---- candidate scan against the histogram at the start of the pixel ---------------
-            // Every lane looks at candidates sub, sub + LPC, ...; the trip count comes from the
-            // strength (warp-uniform), candidates beyond the clamped band are predicated off, and the
-            // body is unrolled so that the independent shared-memory loads are in flight together.
-            // NACC running maxima (merged after the scan) keep the compare chain short where a lane looks
-            // at many candidates.  (BM: only the bytes whose look-up failed come here; need_scan is the
-            // same in all lanes of a channel group and the block contains no warp-level operation.)
-            if (!BM || need_scan) {
-                const int jl = (span - sub) >> C::LOG2LPC;          // last valid j of this lane (-1: none)
-                const unsigned off0 = (unsigned)(lo + sub + rot) * 8u;   // byte offset of candidate j = 0
-                const unsigned low0 = 511u - (unsigned)sub;          // its "511 - pos" field
-                const int jx = ex - lo - sub;                        // j * LPC of the exact symbol, if mine
-                // (BM: only this lane's own candidates - the block runs diverged anyway and a clamped band
-                // is usually short)
-                for (int j0 = 0; j0 < (BM ? jl + 1 : jmax); j0 += C::UNR) {
-                    // per-chunk bases, so that each candidate below only adds compile-time constants
-                    const unsigned off_c = off0 + (unsigned)(j0 * LPC * 8);
-                    const unsigned low_c = low0 - (unsigned)(j0 * LPC);
-                    const int jl_c = jl - j0, jx_c = jx - j0 * LPC;
+                // Only the bytes whose look-up failed scan; need_scan is the same in all lanes of a channel
+                // group and the block contains no warp-level operation.
+                if (need_scan) {
+                    unsigned long long acc[C::NACC];
 #pragma unroll
-                    for (int u = 0; u < C::UNR; u++) {
-                        unsigned long long key = pl_hk_load(hkt, off_c + (unsigned)(u * LPC * 8));
-                        key |= low_c - (unsigned)(u * LPC);          // low 10 bits of an entry are zero
-                        if (!C::EXSEP) key |= (unsigned)(u * LPC == jx_c) << 9;
-                        unsigned long long &a = acc[u % C::NACC];
-                        a = (u <= jl_c && key > a) ? key : a;
-                    }
+                    for (int k = 0; k < C::NACC; k++) acc[k] = 0;
+                    scan(acc);
+#pragma unroll
+                    for (int k = C::NACC / 2; k >= 1; k >>= 1)
+#pragma unroll
+                        for (int m = 0; m < k; m++) acc[m] = acc[m + k] > acc[m] ? acc[m + k] : acc[m];
+                    acc0 = acc[0];
                 }
-            }
-            if (C::EXSEP || BM) {
-                // the exact symbol, with its bonus bit; every lane of the group may add it (max is
-                // idempotent)
-                const int pos = ex - lo;
-                const unsigned long long key =
-                    pl_hk_load(hkt, (unsigned)(ex + rot) * 8u) | pl_key_low(true, pos & 255);
-                unsigned long long &a = acc[C::NACC - 1];
-                a = (pos >= 0 && pos <= span && key > a) ? key : a;
-            }
+                exact_candidate(acc0);
+            } else {
+                unsigned long long acc[C::NACC];
 #pragma unroll
-            for (int k = C::NACC / 2; k >= 1; k >>= 1)
+                for (int k = 0; k < C::NACC; k++) acc[k] = 0;
+                scan(acc);
+                if (C::EXSEP) exact_candidate(acc[C::NACC - 1]);
 #pragma unroll
-                for (int m = 0; m < k; m++) acc[m] = acc[m + k] > acc[m] ? acc[m + k] : acc[m];
-            unsigned long long bkey = acc[0];
+                for (int k = C::NACC / 2; k >= 1; k >>= 1)
+#pragma unroll
+                    for (int m = 0; m < k; m++) acc[m] = acc[m + k] > acc[m] ? acc[m + k] : acc[m];
+                acc0 = acc[0];
+            }
+            unsigned long long bkey = acc0;
 #pragma unroll
             for (int mk = 1; mk < LPC; mk <<= 1) {
                 const unsigned long long okey = __shfl_xor_sync(PL_FULL, bkey, mk);
@@ -637,14 +652,18 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC, BM> &sm
                     // field of bkey is the symbol's count just before this channel's increment (the replay
                     // and the dup correction above keep it so).
                     const unsigned now = (unsigned)(bkey >> 32) + 1u;
-                    const unsigned rank = ((unsigned)bkey >> PL_KEY_RANK_SHIFT) & 255u;
+                    const unsigned rank7 = ((unsigned)bkey >> (PL_KEY_RANK_SHIFT - 7)) & (255u << 7);   // rank << 7
                     const int s8 = (int)(signed char)sym;   // the histogram bin, as a symbol in [-128, 127]
-                    const unsigned ks = pl_udiv_magic((unsigned)(s8 < 0 ? -s8 : s8), step_magic);
+                    const unsigned as8 = (unsigned)(s8 < 0 ? -s8 : s8);
+                    const unsigned ks = pl_udiv_magic(as8, step_magic);
+                    const int rs = (int)(as8 - ks * (unsigned)step);            // |s8| mod step
                     const int t1 = (int)ks + (s8 < 0 ? bmc.P1 : 0);
                     unsigned *e1 = (unsigned *)&bmrow[t1];
                     const unsigned base1 = t1 == tl ? base_l : *(volatile unsigned *)(e1 + 1);
-                    if (now >= base1)
-                        atomicMax(e1, pl_bm_key(now - base1, rank, s8 - pl_bm_low(bmc, t1, step)));
+                    // position in the bucket: rs from its first symbol (s8 >= 0), q - rs (s8 < 0)
+                    const unsigned key1 = ((now - base1) << PL_BM_COUNT_SHIFT) | rank7 |
+                                          (unsigned)(127 - (s8 < 0 ? q - rs : rs));
+                    if (now >= base1) atomicMax(e1, key1);
                     if (s8 >= bmc.seam_p || s8 <= bmc.seam_n) {
                         PL_EMU_COUNT(PL_CNT_BM_GENERAL);
                         // bins >= seam_p: also symbol s8 - 256 of the last negative bucket;
@@ -654,8 +673,8 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC, BM> &sm
                         unsigned *e2 = (unsigned *)&bmrow[t2];
                         const unsigned base2 = *(volatile unsigned *)(e2 + 1);
                         if (now >= base2)
-                            atomicMax(e2, pl_bm_key(now - base2, rank,
-                                                    s8 + (up ? 256 : -256) - pl_bm_low(bmc, t2, step)));
+                            atomicMax(e2, ((now - base2) << PL_BM_COUNT_SHIFT) | rank7 |
+                                              (unsigned)(127 - (s8 + (up ? 256 : -256) - pl_bm_low(bmc, t2, step))));
                     } else {
                         PL_EMU_COUNT(PL_CNT_BM_FASTUPD);
                     }
