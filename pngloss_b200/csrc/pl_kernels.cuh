@@ -151,6 +151,9 @@ struct PlCfg {
     // the Sierra tap table pays off where the kernel is instruction bound (wide lane groups, many CTAs per
     // SM: +8 %); with one or two warps per sub-partition its load latency costs more than it saves (-4 %)
     static const bool DLUT = LPC >= 4;
+    // the narrow mappings have no room for that table (two CTAs of 112 KB per SM) and no taste for its vote;
+    // they use a 1 KB table of 6-bit fields for |error| < 128 and fall back per lane
+    static const bool DL32 = LPC <= 2;
     // bank stagger between the histograms of the chains of one warp (64-bit entries, rotation)
     static const int HROT = LPC == 2 ? 8 : LPC == 1 ? 4 : 0;
 };
@@ -172,6 +175,7 @@ struct PlWarpSmem {
 
 #define PL_K2_SMEM_ALIGN 2048
 #define PL_DLUT_HALF 512   /* the Sierra tap table covers error values -512 .. 511 (see pl_pack_taps) */
+#define PL_DL32_HALF 128   /* the small one -128 .. 127 (see pl_pack_taps6) */
 
 // Bucket-maxima variant (BM): number of entries of PlCtaSmem::bmk per (chain, filter).  Buckets exist
 // for strength + 1 >= 16 (see pl_bm_counts), which gives at most 128/16 + 1 + 129/16 + 1 = 18 of them.
@@ -193,6 +197,7 @@ struct PlCtaSmem {
     // table of chain ci is stored rotated by ci * HROT entries to land in different banks.
     unsigned long long hk[PlCfg<LPC>::CPW][PL_FILTERS * 256];
     unsigned long long dlut[PlCfg<LPC>::DLUT ? 2 * PL_DLUT_HALF : 1];   // packed Sierra taps by error value
+    unsigned dl32[PlCfg<LPC>::DL32 ? 2 * PL_DL32_HALF : 1];              // the same, 5 x 6 bits (pl_pack_taps6)
     uint32_t base[PlCfg<LPC>::CPW][256];              // symbol_frequency at the start of the row
     // BM: per chain, filter and band ("bucket") of the symbol axis the candidate key of the symbol that
     // currently wins the choice inside that band (see pl_row_pass)
@@ -239,6 +244,22 @@ __device__ __forceinline__ PlTaps pl_unpack_taps(unsigned long long e) {
     t.fours = (int)(signed char)(lo >> 16);
     t.five = (int)(signed char)(lo >> 24);
     t.rem = (int)(signed char)(unsigned)(e >> 32);
+    return t;
+}
+
+// For |diff| < PL_DL32_HALF every value lies in [-32, 31] (|d| <= 127: twos <= 7, threes <= 12, fours <= 16,
+// five <= 21, rem <= 22), so the five of them fit one 32-bit word as 6-bit fields biased by 32.
+__device__ __forceinline__ unsigned pl_pack_taps6(const PlTaps &t) {
+    return (unsigned)(t.twos + 32) | ((unsigned)(t.threes + 32) << 6) | ((unsigned)(t.fours + 32) << 12) |
+           ((unsigned)(t.five + 32) << 18) | ((unsigned)(t.rem + 32) << 24);
+}
+__device__ __forceinline__ PlTaps pl_unpack_taps6(unsigned e) {
+    PlTaps t;
+    t.twos = (int)(e & 63u) - 32;
+    t.threes = (int)((e >> 6) & 63u) - 32;
+    t.fours = (int)((e >> 12) & 63u) - 32;
+    t.five = (int)((e >> 18) & 63u) - 32;
+    t.rem = (int)(e >> 24) - 32;
     return t;
 }
 
@@ -690,6 +711,9 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC, BM> &sm
             if (C::DLUT && __all_sync(PL_FULL, (unsigned)(diff + PL_DLUT_HALF) < 2u * PL_DLUT_HALF)) {
                 PL_EMU_COUNT(PL_CNT_TAPS_TABLE);
                 tp = pl_unpack_taps(sm.dlut[diff + PL_DLUT_HALF]);
+            } else if (C::DL32 && (unsigned)(diff + PL_DL32_HALF) < 2u * PL_DL32_HALF) {   // per lane
+                PL_EMU_COUNT(PL_CNT_TAPS_TABLE);
+                tp = pl_unpack_taps6(sm.dl32[diff + PL_DL32_HALF]);
             } else {
                 PL_EMU_COUNT(PL_CNT_TAPS_COMPUTED);
                 tp = pl_sierra_taps(diff, bleed_magic);
@@ -957,6 +981,9 @@ pl_k2_quantize(const PlImageDev *imgs, const int *slots, int strength, int bleed
     if (C::DLUT)
         for (int k = tid; k < 2 * PL_DLUT_HALF; k += PL_K2_THREADS)
             sm.dlut[k] = pl_pack_taps(pl_sierra_taps(k - PL_DLUT_HALF, bleed_magic));
+    if (C::DL32)
+        for (int k = tid; k < 2 * PL_DL32_HALF; k += PL_K2_THREADS)
+            sm.dl32[k] = pl_pack_taps6(pl_sierra_taps(k - PL_DL32_HALF, bleed_magic));
     __syncthreads();
     int prev_w = 0;
 #ifdef PL_K2_PROFILE

@@ -109,11 +109,12 @@ def test_emu_both_variants_of_each_path_ran(emu, oracle):
     variant of the channel fix-up; all four must have run (and stayed bit-exact)."""
     before = emu.counters()
     smooth = oracle.synth(40, 24, 5)
-    compare(emu, oracle, [smooth], 20, 2, False, 8)          # lanes 8: taps from the table
-    compare(emu, oracle, [smooth, smooth], 20, 2, False, 1)  # lanes 1: taps computed
+    compare(emu, oracle, [smooth], 20, 2, False, 8)          # lanes 8: taps from the 64-bit table
+    compare(emu, oracle, [smooth, smooth], 20, 2, False, 1)  # lanes 1: taps from the 6-bit table
     rng = np.random.default_rng(3)
     noisy = rng.integers(0, 256, (8, 24, 4), dtype=np.uint8)
-    compare(emu, oracle, [noisy], 255, 1, False, 8)          # errors beyond the table range
+    compare(emu, oracle, [noisy], 255, 1, False, 8)          # errors beyond the range of either table:
+    compare(emu, oracle, [noisy], 255, 1, False, 1)          # taps computed
     after = emu.counters()
     for key in ("taps_table", "taps_computed", "fixup_replay", "fixup_skipped"):
         assert after[key] > before[key], key
