@@ -160,6 +160,20 @@ int pngloss_b200_batch_timings(pngloss_b200_batch *b, float ms[4]);
  * [3] kernels launched (bits 0-7) and, bit 8, whether the quantise kernel used the bucket-maxima table. */
 int pngloss_b200_batch_launch_info(pngloss_b200_batch *b, uint32_t info[4]);
 
+/* Filtered PNG scanlines of the batch's results, ready for deflate (what the reference leaves to libpng
+ * after the hot path, src/rwpng.c:488-495,557-613): for every image the colour type its output pixels allow
+ * (1 gray, 2 gray+alpha, 3 rgb, 4 rgba bytes per pixel), and height rows of one filter-type byte plus
+ * width * bytes_per_pixel filtered bytes - row 0 filtered by libpng's minimum-sum-of-absolute-differences
+ * heuristic, every other row by the filter the search chose.  Asynchronous; call after pngloss_b200_batch_run.
+ * The first call allocates a second device buffer of height * (1 + 4 * width) bytes per image. */
+int pngloss_b200_batch_scanlines(pngloss_b200_batch *b);
+/* Waits for the stream.  Each out pointer may be NULL; milliseconds = device time of the two scanline
+ * kernels of the last call. */
+int pngloss_b200_batch_scanline_info(pngloss_b200_batch *b, size_t i, uint32_t *bytes_per_pixel,
+                                     uint32_t *row0_filter, size_t *bytes, float *milliseconds);
+int pngloss_b200_batch_download_scanlines(pngloss_b200_batch *b, size_t i, unsigned char *dst,
+                                          size_t capacity);   /* async copy of `bytes` bytes */
+
 #ifdef __cplusplus
 }
 #endif

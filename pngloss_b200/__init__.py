@@ -37,7 +37,8 @@ EXPORTS = [
     "pngloss_b200_batch_download_input", "pngloss_b200_batch_finish",
     "pngloss_b200_batch_image_histogram", "pngloss_b200_batch_histogram",
     "pngloss_b200_batch_histogram_device", "pngloss_b200_batch_timings",
-    "pngloss_b200_batch_launch_info",
+    "pngloss_b200_batch_launch_info", "pngloss_b200_batch_scanlines", "pngloss_b200_batch_scanline_info",
+    "pngloss_b200_batch_download_scanlines",
 ]
 
 
@@ -63,6 +64,7 @@ class ImageDesc(ctypes.Structure):
 
 
 _lib = None
+u32t = ctypes.c_uint32
 
 
 def load_library() -> ctypes.CDLL:
@@ -123,6 +125,10 @@ def load_library() -> ctypes.CDLL:
     L.pngloss_b200_batch_histogram_device.restype = vp
     L.pngloss_b200_batch_timings.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     L.pngloss_b200_batch_launch_info.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32)]
+    L.pngloss_b200_batch_scanlines.argtypes = [vp]
+    L.pngloss_b200_batch_scanline_info.argtypes = [vp, sz, ctypes.POINTER(u32), ctypes.POINTER(u32),
+                                                   ctypes.POINTER(sz), ctypes.POINTER(ctypes.c_float)]
+    L.pngloss_b200_batch_download_scanlines.argtypes = [vp, sz, vp, sz]
     _lib = L
     return L
 
@@ -373,6 +379,24 @@ class Batch:
         self.ctx._check(self.lib.pngloss_b200_batch_launch_info(self.handle, info))
         return dict(k2_ctas=info[0], images_per_cta=info[1], k2_smem_bytes=info[2], launches=info[3] & 0xff,
                     bucket_maxima=bool(info[3] & 0x100))
+
+    def scanlines(self):
+        """K4: filtered PNG scanlines of the results, on the device (asynchronous)."""
+        self.ctx._check(self.lib.pngloss_b200_batch_scanlines(self.handle))
+
+    def scanline_info(self, i):
+        bpp, f0, nbytes, ms = u32t(), u32t(), ctypes.c_size_t(), ctypes.c_float()
+        self.ctx._check(self.lib.pngloss_b200_batch_scanline_info(
+            self.handle, i, ctypes.byref(bpp), ctypes.byref(f0), ctypes.byref(nbytes), ctypes.byref(ms)))
+        return dict(bytes_per_pixel=bpp.value, row0_filter=f0.value, bytes=nbytes.value, k4_ms=ms.value)
+
+    def download_scanlines(self, i) -> np.ndarray:
+        """(height, 1 + width * bytes_per_pixel) uint8: filter-type byte, then the filtered row."""
+        info = self.scanline_info(i)
+        buf = np.empty(info["bytes"], np.uint8)
+        self.ctx._check(self.lib.pngloss_b200_batch_download_scanlines(self.handle, i, buf.ctypes.data, buf.size))
+        self.ctx.sync()
+        return buf.reshape(int(self.heights[i]), -1)
 
     def close(self):
         if self.handle:

@@ -58,6 +58,13 @@ struct pngloss_b200_batch {
     uint32_t info[4] = {0, 0, 0, 0};
     bool desc_dirty = true;
     bool in_place = false;               // PNGLOSS_B200_BATCH_IN_PLACE: out aliases in
+    // K4 (filtered scanlines): second slab, allocated by the first pngloss_b200_batch_scanlines call
+    unsigned char *scan_slab = nullptr;
+    PlScanDev *dscan = nullptr;
+    uint32_t *oflags = nullptr, *hoflags = nullptr;   // [n][4]; hoflags pinned
+    std::vector<size_t> scan_off;
+    cudaEvent_t ev_scan[2] = {nullptr, nullptr};
+    bool scan_ran = false;
     // job API
     bool busy = false;
     cudaEvent_t ev_up = nullptr, ev_done = nullptr, ev_down = nullptr;
@@ -334,6 +341,10 @@ extern "C" void pngloss_b200_batch_destroy(pngloss_b200_batch *b) {
     if (b->slab) cudaFree(b->slab);
     if (b->hstatus) cudaFreeHost(b->hstatus);
     if (b->hfilters) cudaFreeHost(b->hfilters);
+    if (b->scan_slab) cudaFree(b->scan_slab);
+    if (b->hoflags) cudaFreeHost(b->hoflags);
+    for (int k = 0; k < 2; k++)
+        if (b->ev_scan[k]) cudaEventDestroy(b->ev_scan[k]);
     delete b;
 }
 
@@ -637,6 +648,87 @@ extern "C" int pngloss_b200_batch_timings(pngloss_b200_batch *b, float ms[4]) {
 extern "C" int pngloss_b200_batch_launch_info(pngloss_b200_batch *b, uint32_t info[4]) {
     if (!b || !info) return PNGLOSS_B200_INVALID_ARGUMENT;
     memcpy(info, b->info, sizeof b->info);
+    return PNGLOSS_B200_SUCCESS;
+}
+
+// ---- K4: filtered scanlines ---------------------------------------------------------------------------------
+extern "C" int pngloss_b200_batch_scanlines(pngloss_b200_batch *b) {
+    if (!b) return PNGLOSS_B200_INVALID_ARGUMENT;
+    pngloss_b200_ctx *ctx = b->ctx;
+    if (!b->ran) return set_err(ctx, PNGLOSS_B200_INVALID_ARGUMENT, "scanlines: the batch has not been run");
+    PL_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = b->n;
+    if (!b->scan_slab) {
+        // worst case 4 bytes per pixel; the colour type is only known once the output has been scanned
+        size_t off = 0;
+        auto take = [&](size_t bytes, size_t al) { off = align_up(off, al); size_t o = off; off += bytes; return o; };
+        const size_t o_desc = take(n * sizeof(PlScanDev), 256);
+        const size_t o_flags = take(n * 4 * sizeof(uint32_t), 256);
+        b->scan_off.resize(n);
+        for (size_t i = 0; i < n; i++) b->scan_off[i] = take((size_t)b->h[i] * (1 + (size_t)b->w[i] * 4), 256);
+        cudaError_t e = cudaMalloc((void **)&b->scan_slab, align_up(off, 256));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            b->scan_slab = nullptr;
+            return set_err(ctx, PNGLOSS_B200_OUT_OF_MEMORY, "cudaMalloc(%zu bytes of scanlines) failed", off);
+        }
+        b->dscan = (PlScanDev *)(b->scan_slab + o_desc);
+        b->oflags = (uint32_t *)(b->scan_slab + o_flags);
+        if (cudaMallocHost((void **)&b->hoflags, n * 4 * sizeof(uint32_t)) != cudaSuccess ||
+            cudaEventCreate(&b->ev_scan[0]) != cudaSuccess || cudaEventCreate(&b->ev_scan[1]) != cudaSuccess)
+            return set_err(ctx, PNGLOSS_B200_OUT_OF_MEMORY, "scanlines: host-side allocation failed");
+        std::vector<PlScanDev> h(n);
+        for (size_t i = 0; i < n; i++) {
+            h[i].px = b->himgs[i].out;
+            h[i].filters = b->himgs[i].filters;
+            h[i].scan = b->scan_slab + b->scan_off[i];
+            h[i].oflags = b->oflags + i * 4;
+            h[i].width = b->w[i];
+            h[i].height = b->h[i];
+        }
+        PL_CUDA(ctx, cudaMemcpyAsync(b->dscan, h.data(), n * sizeof(PlScanDev), cudaMemcpyHostToDevice, b->stream));
+        PL_CUDA(ctx, cudaStreamSynchronize(b->stream));   // h goes out of scope
+    }
+    PL_CUDA(ctx, cudaMemsetAsync(b->oflags, 0, n * 4 * sizeof(uint32_t), b->stream));
+    uint32_t hmin = b->h[0];
+    for (size_t i = 1; i < n; i++) hmin = std::min(hmin, b->h[i]);
+    const size_t want = (8 * 148 + n - 1) / n;   // ~8 CTAs of 256 threads per SM
+    const unsigned slices = (unsigned)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(want, 1024), hmin));
+    PL_CUDA(ctx, cudaEventRecord(b->ev_scan[0], b->stream));
+    pl_k4_scan_output<<<(unsigned)(n * slices), PL_K4_THREADS, 0, b->stream>>>(b->dscan, slices);
+    PL_CUDA(ctx, cudaGetLastError());
+    pl_k4_scanlines<<<(unsigned)(n * slices), PL_K4_THREADS, 0, b->stream>>>(b->dscan, slices);
+    PL_CUDA(ctx, cudaGetLastError());
+    PL_CUDA(ctx, cudaEventRecord(b->ev_scan[1], b->stream));
+    PL_CUDA(ctx, cudaMemcpyAsync(b->hoflags, b->oflags, n * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
+    b->scan_ran = true;
+    return PNGLOSS_B200_SUCCESS;
+}
+
+extern "C" int pngloss_b200_batch_scanline_info(pngloss_b200_batch *b, size_t i, uint32_t *bytes_per_pixel,
+                                                uint32_t *row0_filter, size_t *bytes, float *milliseconds) {
+    if (!b || i >= b->n || !b->scan_ran) return PNGLOSS_B200_INVALID_ARGUMENT;
+    pngloss_b200_ctx *ctx = b->ctx;
+    PL_CUDA(ctx, cudaSetDevice(ctx->device));
+    PL_CUDA(ctx, cudaStreamSynchronize(b->stream));
+    const uint32_t *f = b->hoflags + i * 4;
+    const uint32_t bpp = f[0] ? (f[1] ? 4u : 3u) : (f[1] ? 2u : 1u);
+    if (bytes_per_pixel) *bytes_per_pixel = bpp;
+    if (row0_filter) *row0_filter = f[2];
+    if (bytes) *bytes = (size_t)b->h[i] * (1 + (size_t)b->w[i] * bpp);
+    if (milliseconds) PL_CUDA(ctx, cudaEventElapsedTime(milliseconds, b->ev_scan[0], b->ev_scan[1]));
+    return PNGLOSS_B200_SUCCESS;
+}
+
+extern "C" int pngloss_b200_batch_download_scanlines(pngloss_b200_batch *b, size_t i, unsigned char *dst,
+                                                     size_t capacity) {
+    if (!b || i >= b->n || !dst || !b->scan_ran) return PNGLOSS_B200_INVALID_ARGUMENT;
+    pngloss_b200_ctx *ctx = b->ctx;
+    size_t bytes = 0;
+    int rc = pngloss_b200_batch_scanline_info(b, i, nullptr, nullptr, &bytes, nullptr);
+    if (rc) return rc;
+    if (capacity < bytes) return set_err(ctx, PNGLOSS_B200_INVALID_ARGUMENT, "scanlines: buffer too small");
+    PL_CUDA(ctx, cudaMemcpyAsync(dst, b->scan_slab + b->scan_off[i], bytes, cudaMemcpyDeviceToHost, b->stream));
     return PNGLOSS_B200_SUCCESS;
 }
 

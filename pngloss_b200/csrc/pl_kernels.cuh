@@ -1109,6 +1109,153 @@ __global__ void __launch_bounds__(256) pl_k3_batch_hist(const PlImageDev *imgs, 
 }
 
 // --------------------------------------------------------------------------------------------------
+// K4: filtered PNG scanlines of the quantised images, ready for deflate.
+//
+// What the reference leaves to libpng after the hot path (src/rwpng.c:557-613 colour type auto-detection,
+// :488-495 row filters): narrow the RGBA rows to the colour type the *output* pixels allow (gray /
+// gray+alpha / rgb / rgba), apply to every row the filter the search chose - row 0: libpng's
+// min-sum-of-absolute-differences heuristic, as the reference's writer does - and lay the rows out as zlib
+// wants them: one filter-type byte, then width * bpp filtered bytes.
+//   pl_k4_scan_output: the gray / opaque scan of the output.  4 B/pixel read.
+//   pl_k4_scanlines:   grid = images * slices CTAs of 256 threads; CTA b takes rows (b % slices),
+//                      (b % slices) + slices, ... of image b / slices.  4 B/pixel read (the three neighbours
+//                      come from L1/L2), bpp B/pixel written through a shared-memory stage as aligned words.
+// --------------------------------------------------------------------------------------------------
+#define PL_K4_THREADS 256
+
+__global__ void __launch_bounds__(PL_K4_THREADS) pl_k4_scan_output(const PlScanDev *imgs, unsigned slices) {
+    const PlScanDev im = imgs[blockIdx.x / slices];
+    const size_t n = (size_t)im.width * im.height;
+    unsigned notgray = 0, notopaque = 0;
+    for (size_t i = (size_t)(blockIdx.x % slices) * PL_K4_THREADS + threadIdx.x; i < n;
+         i += (size_t)slices * PL_K4_THREADS) {
+        const uchar4 p = im.px[i];
+        notgray |= (unsigned)(p.x != p.y || p.y != p.z);
+        notopaque |= (unsigned)(p.w < 255);
+    }
+    if (__any_sync(PL_FULL, notgray) && (threadIdx.x & 31) == 0) atomicOr(&im.oflags[0], 1u);
+    if (__any_sync(PL_FULL, notopaque) && (threadIdx.x & 31) == 0) atomicOr(&im.oflags[1], 1u);
+}
+
+// bytes of a pixel in the narrowed layout: byte selector for __byte_perm (gray: G; gray+alpha: G,A; ...)
+__device__ __forceinline__ unsigned pl_k4_narrow(unsigned rgba, int bpp) {
+    return bpp == 1 ? __byte_perm(rgba, 0u, 0x4441u) : bpp == 2 ? __byte_perm(rgba, 0u, 0x4431u) : rgba;
+}
+// the bpp filtered bytes of one pixel, packed into the low bytes of a word
+__device__ __forceinline__ unsigned pl_k4_filter_pixel(int type, int bpp, unsigned cur, unsigned left, unsigned up,
+                                                       unsigned ul) {
+    unsigned r = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        if (c < bpp) {
+            const int x = pl_byte(cur, c), a = pl_byte(left, c), b = pl_byte(up, c), d = pl_byte(ul, c);
+            const int pred = type == 1 ? a : type == 2 ? b : type == 3 ? (a + b) >> 1 : type == 4 ? pl_paeth(b, d, a) : 0;
+            r |= ((unsigned)(x - pred) & 255u) << (8 * c);
+        }
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(PL_K4_THREADS) pl_k4_scanlines(const PlScanDev *imgs, unsigned slices) {
+    // staging of one segment: up to 256 pixels * 4 bytes, shifted by the misalignment of its destination
+    __shared__ __align__(16) unsigned char stage[PL_K4_THREADS * 4 + 8];
+    __shared__ unsigned red[5][PL_K4_THREADS / 32];
+    __shared__ int row0_type;
+    const PlScanDev im = imgs[blockIdx.x / slices];
+    const int W = (int)im.width, H = (int)im.height;
+    const bool gray = im.oflags[0] == 0, opaque = im.oflags[1] == 0;
+    const int bpp = gray ? (opaque ? 1 : 2) : (opaque ? 3 : 4);
+    const size_t stride = 1 + (size_t)W * bpp;
+    const int tid = threadIdx.x;
+
+    for (int y = (int)(blockIdx.x % slices); y < H; y += (int)slices) {
+        const uchar4 *row = im.px + (size_t)y * W;
+        const uchar4 *above = row - W;   // only read when y > 0
+        int type;
+        if (y == 0) {
+            // libpng's heuristic on row 0 (reference src/rwpng.c:488-495 leaves it to libpng): the filter
+            // with the smallest sum of |signed residual|, first minimum in the order none .. paeth
+            unsigned sum[5] = {0, 0, 0, 0, 0};
+            for (int x = tid; x < W; x += PL_K4_THREADS) {
+                const unsigned cur = pl_k4_narrow(pl_u32(row[x]), bpp);
+                const unsigned left = x ? pl_k4_narrow(pl_u32(row[x - 1]), bpp) : 0u;
+#pragma unroll
+                for (int f = 0; f < 5; f++) {
+                    const unsigned r = pl_k4_filter_pixel(f, bpp, cur, left, 0u, 0u);
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+                        if (c < bpp) {
+                            const unsigned v = (r >> (8 * c)) & 255u;
+                            sum[f] += v < 128u ? v : 256u - v;
+                        }
+                }
+            }
+#pragma unroll
+            for (int f = 0; f < 5; f++) {
+#pragma unroll
+                for (int mk = 16; mk >= 1; mk >>= 1) sum[f] += __shfl_xor_sync(PL_FULL, sum[f], mk);
+                if ((tid & 31) == 0) red[f][tid >> 5] = sum[f];
+            }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned best = ~0u;
+                int pick = 0;
+                for (int f = 0; f < 5; f++) {
+                    unsigned t = 0;
+                    for (int k = 0; k < PL_K4_THREADS / 32; k++) t += red[f][k];
+                    if (t < best) { best = t; pick = f; }
+                }
+                row0_type = pick;
+                im.oflags[2] = (unsigned)pick;
+            }
+            __syncthreads();
+            type = row0_type;
+        } else {
+            const unsigned m = im.filters[y];
+            type = m == 0x10 ? 1 : m == 0x20 ? 2 : m == 0x40 ? 3 : m == 0x80 ? 4 : 0;
+        }
+        unsigned char *dst_row = im.scan + (size_t)y * stride;
+        if (tid == 0) dst_row[0] = (unsigned char)type;
+        for (int x0 = 0; x0 < W; x0 += PL_K4_THREADS) {
+            const int npx = min(PL_K4_THREADS, W - x0);
+            unsigned char *g0 = dst_row + 1 + (size_t)x0 * bpp;          // destination of this segment
+            const unsigned mis = (unsigned)((size_t)g0 & 3u);            // stage[mis + i] <-> g0[i]
+            const int len = npx * bpp;
+            if (tid < npx) {
+                const int x = x0 + tid;
+                const unsigned cur = pl_k4_narrow(pl_u32(row[x]), bpp);
+                const unsigned left = x ? pl_k4_narrow(pl_u32(row[x - 1]), bpp) : 0u;
+                unsigned up = 0, ul = 0;
+                if (y) {
+                    up = pl_k4_narrow(pl_u32(above[x]), bpp);
+                    ul = x ? pl_k4_narrow(pl_u32(above[x - 1]), bpp) : 0u;
+                }
+                const unsigned r = pl_k4_filter_pixel(type, bpp, cur, left, up, ul);
+                unsigned char *s = stage + mis + tid * bpp;
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    if (c < bpp) s[c] = (unsigned char)(r >> (8 * c));
+            }
+            __syncthreads();
+            // aligned words of [g0 - mis, g0 + len): whole words as 32-bit stores, the ragged ends bytewise
+            const int nwords = ((int)mis + len + 3) >> 2;
+            for (int wi = tid; wi < nwords; wi += PL_K4_THREADS) {
+                const int b0 = wi * 4;                                   // offset in stage
+                if (b0 >= (int)mis && b0 + 4 <= (int)mis + len) {
+                    *(unsigned *)(g0 - mis + b0) = *(const unsigned *)(stage + b0);
+                } else {
+                    for (int k = 0; k < 4; k++) {
+                        const int o = b0 + k;
+                        if (o >= (int)mis && o < (int)mis + len) g0[o - (int)mis] = stage[o];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
 // Synthetic gradient + noise RGBA image, identical to oracle_synth_rgba.
 // --------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long pl_splitmix64(unsigned long long z) {

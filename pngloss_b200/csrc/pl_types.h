@@ -36,3 +36,13 @@ struct PlImageDev {
 
 // active RGBA channels of a colour mode: 1 gray (G), 2 gray+alpha (G,A), 3 rgb, 4 rgba
 #define PL_MODE_MASK(mode) ((mode) == 1 ? 0x2 : (mode) == 2 ? 0xA : (mode) == 3 ? 0x7 : 0xF)
+
+// One image as the scanline kernels (K4) see it.
+struct PlScanDev {
+    const uchar4 *px;              // quantised image (K2's output), tight RGBA8 rows
+    const unsigned char *filters;  // K2's row filters (libpng masks)
+    unsigned char *scan;           // out: height x (1 + width * bytes_per_pixel) bytes, filter byte first
+    uint32_t *oflags;              // [0] != 0: some output pixel is not gray; [1] != 0: not opaque;
+                                   // [2] out: filter type used for row 0
+    uint32_t width, height;
+};

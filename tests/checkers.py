@@ -150,3 +150,69 @@ def to_bpp(rgba: np.ndarray, bpp: int) -> np.ndarray:
     if bpp in (1, 3):
         a[..., 3] = 255
     return a
+
+
+# ---- PNG scanlines (K4): plain restatement of the PNG specification's filters -----------------------------
+def png_narrow(rgba: np.ndarray):
+    """RGBA8 (h, w, 4) -> (bytes_per_pixel, packed (h, w * bpp)) with the colour type the pixels allow, the
+    way the reference's writer detects it (src/rwpng.c:557-613)."""
+    gray = bool((rgba[..., 0] == rgba[..., 1]).all() and (rgba[..., 1] == rgba[..., 2]).all())
+    opaque = bool((rgba[..., 3] == 255).all())
+    chans = {(True, True): [1], (True, False): [1, 3], (False, True): [0, 1, 2], (False, False): [0, 1, 2, 3]}[
+        (gray, opaque)]
+    return len(chans), np.ascontiguousarray(rgba[..., chans]).reshape(rgba.shape[0], -1)
+
+
+def png_filter_row(ftype: int, row: np.ndarray, prev, bpp: int) -> np.ndarray:
+    row = row.astype(np.int32)
+    up = np.zeros_like(row) if prev is None else prev.astype(np.int32)
+    left = np.concatenate([np.zeros(bpp, np.int32), row[:-bpp]]) if row.size > bpp else np.zeros_like(row)
+    ul = np.concatenate([np.zeros(bpp, np.int32), up[:-bpp]]) if row.size > bpp else np.zeros_like(row)
+    if ftype == 0:
+        pred = np.zeros_like(row)
+    elif ftype == 1:
+        pred = left
+    elif ftype == 2:
+        pred = up
+    elif ftype == 3:
+        pred = (left + up) >> 1
+    else:
+        p = left + up - ul
+        pa, pb, pc = np.abs(p - left), np.abs(p - up), np.abs(p - ul)
+        pred = np.where((pa <= pb) & (pa <= pc), left, np.where(pb <= pc, up, ul))
+    return ((row - pred) & 255).astype(np.uint8)
+
+
+def png_heuristic_filter(row: np.ndarray, prev, bpp: int) -> int:
+    """libpng's default: smallest sum of |signed residual|, first minimum in the order none .. paeth."""
+    sums = []
+    for f in range(5):
+        r = png_filter_row(f, row, prev, bpp).astype(np.int64)
+        sums.append(int(np.where(r < 128, r, 256 - r).sum()))
+    return int(np.argmin(sums))
+
+
+def png_scanlines(rgba: np.ndarray, row_filters: np.ndarray):
+    """What the reference's writer hands to deflate for a quantised image: -> (bpp, row0 filter, (h, 1 + w*bpp))."""
+    bpp, packed = png_narrow(rgba)
+    h = packed.shape[0]
+    out = np.zeros((h, 1 + packed.shape[1]), np.uint8)
+    types = {0x08: 0, 0x10: 1, 0x20: 2, 0x40: 3, 0x80: 4}
+    f0 = png_heuristic_filter(packed[0], None, bpp)
+    for y in range(h):
+        t = f0 if y == 0 else types[int(row_filters[y])]
+        out[y, 0] = t
+        out[y, 1:] = png_filter_row(t, packed[y], packed[y - 1] if y else None, bpp)
+    return bpp, f0, out
+
+
+def png_from_scanlines(w: int, h: int, bpp: int, scan: np.ndarray) -> bytes:
+    """A complete PNG file around filtered scanlines (zlib here; the product's writer is pl_png.c)."""
+    import struct
+    import zlib
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data))
+    ctype = {1: 0, 2: 4, 3: 2, 4: 6}[bpp]
+    return (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, ctype, 0, 0, 0)) +
+            chunk(b"IDAT", zlib.compress(scan.tobytes(), 6)) + chunk(b"IEND", b""))

@@ -42,6 +42,27 @@ class Emu:
         return dict(pixels=buf, filters=filt, final_hist=final, status=status, batch_hist=batch,
                     chan_hist=chan)
 
+    def scanlines(self, imgs, filters):
+        """K4 on quantised images (list of equally sized (h, w, 4) arrays) and their row filters (n, h):
+        -> list of (bytes_per_pixel, row0_filter, (h, 1 + w * bpp) uint8 array)."""
+        n = len(imgs)
+        h, w, _ = imgs[0].shape
+        buf = np.ascontiguousarray(np.stack(imgs))
+        filt = np.ascontiguousarray(np.asarray(filters, np.uint8).reshape(n, h))
+        room = h * (1 + 4 * w)
+        scan = np.full((n, room), 0x5A, np.uint8)
+        oflags = np.zeros((n, 4), np.uint32)
+        self.lib.emu_scanlines.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        assert self.lib.emu_scanlines(buf.ctypes.data, n, w, h, filt.ctypes.data, scan.ctypes.data,
+                                      oflags.ctypes.data) == 0
+        out = []
+        for i in range(n):
+            bpp = (4 if oflags[i, 1] else 3) if oflags[i, 0] else (2 if oflags[i, 1] else 1)
+            assert (scan[i, h * (1 + w * bpp):] == 0x5A).all(), "K4 wrote past its rows"
+            out.append((bpp, int(oflags[i, 2]), scan[i, :h * (1 + w * bpp)].reshape(h, 1 + w * bpp).copy()))
+        return out
+
     def counters(self):
         """Sierra taps from the table / computed, channel fix-up replays / skips executed so far (per lane)."""
         out = (ctypes.c_ulonglong * 8)()

@@ -76,6 +76,28 @@ extern "C" int emu_optimize(unsigned char *rgba, int n, uint32_t w, uint32_t h,
     return 0;
 }
 
+// K4 on the emulator: pixels = the quantised RGBA images, filters = K2's masks; scan receives, per image,
+// height * (1 + 4 * width) bytes of room (the kernel uses height * (1 + bpp * width) of them).
+extern "C" int emu_scanlines(const unsigned char *rgba, int n, uint32_t w, uint32_t h, const unsigned char *filters,
+                             unsigned char *scan, uint32_t *oflags) {
+    const size_t npx = (size_t)w * h, room = (size_t)h * (1 + 4 * (size_t)w);
+    std::vector<PlScanDev> d(n);
+    memset(oflags, 0, sizeof(uint32_t) * 4 * n);
+    for (int i = 0; i < n; i++) {
+        d[i].px = (const uchar4 *)rgba + npx * i;
+        d[i].filters = filters + (size_t)h * i;
+        d[i].scan = scan + room * i;
+        d[i].oflags = oflags + 4 * (size_t)i;
+        d[i].width = w;
+        d[i].height = h;
+    }
+    const PlScanDev *dd = d.data();
+    const unsigned slices = h < 3 ? h : 3;
+    simt::launch([&] { pl_k4_scan_output(dd, slices); }, dim3(slices * n), dim3(PL_K4_THREADS), 0);
+    simt::launch([&] { pl_k4_scanlines(dd, slices); }, dim3(slices * n), dim3(PL_K4_THREADS), 0);
+    return 0;
+}
+
 extern "C" void emu_synth(unsigned char *dst, uint32_t w, uint32_t h, unsigned long long seed) {
     simt::launch([&] { pl_k_synth((uchar4 *)dst, w, h, seed); }, dim3(3), dim3(256), 0);
 }

@@ -440,3 +440,54 @@ def test_jobs_in_flight_with_separate_outputs(ctx, oracle):
     for _, _, a, b, _, _ in jobs:
         ctx.free_pinned(a)
         ctx.free_pinned(b)
+
+
+
+def test_k4_filtered_scanlines(ctx, oracle):
+    """pngloss_b200_batch_scanlines: the filtered scanlines of the results equal a numpy restatement of the
+    PNG filters applied to the downloaded results, and a PNG decoder turns them back into those pixels."""
+    import io
+
+    from PIL import Image
+
+    from checkers import png_from_scanlines, png_scanlines
+    imgs = [to_bpp(oracle.synth(131, 29, 80 + i), (i % 4) + 1) for i in range(8)]
+    imgs.append(np.full((29, 131, 4), 200, np.uint8))        # flat gray, opaque
+    batch = pngloss_b200.Batch(ctx, [131] * len(imgs), [29] * len(imgs))
+    for i, im in enumerate(imgs):
+        batch.upload(i, im)
+    batch.run(20, 2)
+    batch.scanlines()
+    st, _, _ = batch.finish()
+    assert (st == 0).all()
+    for i, im in enumerate(imgs):
+        out = np.zeros_like(im)
+        rf = np.zeros(29, np.uint8)
+        batch.download(i, out, rf)
+        ctx.sync()
+        info = batch.scanline_info(i)
+        got = batch.download_scanlines(i)
+        want_bpp, want_f0, want = png_scanlines(out, rf)
+        assert (info["bytes_per_pixel"], info["row0_filter"]) == (want_bpp, want_f0), i
+        assert np.array_equal(got, want), i
+        dec = np.asarray(Image.open(io.BytesIO(png_from_scanlines(131, 29, want_bpp, got))).convert("RGBA"))
+        assert np.array_equal(dec, out), i
+    batch.close()
+    # full-size 4K image
+    c = [c for c in cases("large") if c["src"]["w"] == 3840 and c["strength"] == 20][0]
+    src = c["src"]
+    batch = pngloss_b200.Batch(ctx, [src["w"]], [src["h"]])
+    batch.synth(0, src["seed"])
+    batch.run(c["strength"], c["bleed"])
+    batch.scanlines()
+    batch.finish()
+    out = np.zeros((src["h"], src["w"], 4), np.uint8)
+    rf = np.zeros(src["h"], np.uint8)
+    batch.download(0, out, rf)
+    ctx.sync()
+    assert sha16(out) == c["px_sha"]
+    got = batch.download_scanlines(0)
+    want_bpp, want_f0, want = png_scanlines(out, rf)
+    assert batch.scanline_info(0)["bytes_per_pixel"] == want_bpp == 4
+    assert np.array_equal(got, want)
+    batch.close()

@@ -5,7 +5,9 @@ GPU time is spent; the parity tests proper are the -m gpu tests that go through 
 import numpy as np
 import pytest
 
-from checkers import Oracle, to_bpp
+import io
+
+from checkers import Oracle, png_from_scanlines, png_scanlines, to_bpp
 from emu import Emu
 
 
@@ -155,3 +157,23 @@ def test_emu_k1_histograms(emu, oracle):
 def test_emu_synth_matches_oracle(emu, oracle):
     for (w, h, seed) in [(64, 32, 7), (17, 70, 12345), (1, 1, 3)]:
         assert np.array_equal(emu.synth(w, h, seed), oracle.synth(w, h, seed))
+
+
+def test_emu_k4_scanlines(emu, oracle):
+    """K4: colour-type detection on the output, row-0 heuristic, per-row filters, narrowed and filtered
+    scanlines - against a numpy restatement of the PNG filters, and through a real PNG decoder."""
+    from PIL import Image
+    rng = np.random.default_rng(21)
+    for (w, h) in [(37, 9), (1, 5), (300, 4), (256, 3), (5, 1)]:
+        for bpp in (1, 2, 3, 4):
+            src = to_bpp(oracle.synth(w, h, 60 + bpp), bpp) if w > 1 else \
+                to_bpp(rng.integers(0, 256, (h, w, 4), dtype=np.uint8), bpp)
+            px, rf = oracle.optimize(src, 20, 2, True)
+            rf = rf.copy()
+            rf[1:] = rng.choice([0x08, 0x10, 0x20, 0x40, 0x80], size=h - 1)   # every filter type, any row
+            (got_bpp, got_f0, got), = emu.scanlines([px], [rf])
+            want_bpp, want_f0, want = png_scanlines(px, rf)
+            assert (got_bpp, got_f0) == (want_bpp, want_f0), (w, h, bpp)
+            assert np.array_equal(got, want), (w, h, bpp)
+            dec = np.asarray(Image.open(io.BytesIO(png_from_scanlines(w, h, got_bpp, got))).convert("RGBA"))
+            assert np.array_equal(dec, px), (w, h, bpp)
