@@ -168,9 +168,9 @@ int pngloss_b200_batch_launch_info(pngloss_b200_batch *b, uint32_t info[4]);
  * The first call allocates a second device buffer of height * (1 + 4 * width) bytes per image. */
 int pngloss_b200_batch_scanlines(pngloss_b200_batch *b);
 /* Waits for the stream.  Each out pointer may be NULL; milliseconds = device time of the two scanline
- * kernels of the last call. */
+ * kernels of the last call ([0] colour-type scan, [1] filtering). */
 int pngloss_b200_batch_scanline_info(pngloss_b200_batch *b, size_t i, uint32_t *bytes_per_pixel,
-                                     uint32_t *row0_filter, size_t *bytes, float *milliseconds);
+                                     uint32_t *row0_filter, size_t *bytes, float milliseconds[2]);
 int pngloss_b200_batch_download_scanlines(pngloss_b200_batch *b, size_t i, unsigned char *dst,
                                           size_t capacity);   /* async copy of `bytes` bytes */
 

@@ -385,10 +385,11 @@ class Batch:
         self.ctx._check(self.lib.pngloss_b200_batch_scanlines(self.handle))
 
     def scanline_info(self, i):
-        bpp, f0, nbytes, ms = u32t(), u32t(), ctypes.c_size_t(), ctypes.c_float()
+        bpp, f0, nbytes, ms = u32t(), u32t(), ctypes.c_size_t(), (ctypes.c_float * 2)()
         self.ctx._check(self.lib.pngloss_b200_batch_scanline_info(
-            self.handle, i, ctypes.byref(bpp), ctypes.byref(f0), ctypes.byref(nbytes), ctypes.byref(ms)))
-        return dict(bytes_per_pixel=bpp.value, row0_filter=f0.value, bytes=nbytes.value, k4_ms=ms.value)
+            self.handle, i, ctypes.byref(bpp), ctypes.byref(f0), ctypes.byref(nbytes), ms))
+        return dict(bytes_per_pixel=bpp.value, row0_filter=f0.value, bytes=nbytes.value,
+                    k4_scan_ms=ms[0], k4_filter_ms=ms[1])
 
     def download_scanlines(self, i) -> np.ndarray:
         """(height, 1 + width * bytes_per_pixel) uint8: filter-type byte, then the filtered row."""

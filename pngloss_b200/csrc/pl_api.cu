@@ -63,7 +63,7 @@ struct pngloss_b200_batch {
     PlScanDev *dscan = nullptr;
     uint32_t *oflags = nullptr, *hoflags = nullptr;   // [n][4]; hoflags pinned
     std::vector<size_t> scan_off;
-    cudaEvent_t ev_scan[2] = {nullptr, nullptr};
+    cudaEvent_t ev_scan[3] = {nullptr, nullptr, nullptr};
     bool scan_ran = false;
     // job API
     bool busy = false;
@@ -343,7 +343,7 @@ extern "C" void pngloss_b200_batch_destroy(pngloss_b200_batch *b) {
     if (b->hfilters) cudaFreeHost(b->hfilters);
     if (b->scan_slab) cudaFree(b->scan_slab);
     if (b->hoflags) cudaFreeHost(b->hoflags);
-    for (int k = 0; k < 2; k++)
+    for (int k = 0; k < 3; k++)
         if (b->ev_scan[k]) cudaEventDestroy(b->ev_scan[k]);
     delete b;
 }
@@ -675,7 +675,8 @@ extern "C" int pngloss_b200_batch_scanlines(pngloss_b200_batch *b) {
         b->dscan = (PlScanDev *)(b->scan_slab + o_desc);
         b->oflags = (uint32_t *)(b->scan_slab + o_flags);
         if (cudaMallocHost((void **)&b->hoflags, n * 4 * sizeof(uint32_t)) != cudaSuccess ||
-            cudaEventCreate(&b->ev_scan[0]) != cudaSuccess || cudaEventCreate(&b->ev_scan[1]) != cudaSuccess)
+            cudaEventCreate(&b->ev_scan[0]) != cudaSuccess || cudaEventCreate(&b->ev_scan[1]) != cudaSuccess ||
+            cudaEventCreate(&b->ev_scan[2]) != cudaSuccess)
             return set_err(ctx, PNGLOSS_B200_OUT_OF_MEMORY, "scanlines: host-side allocation failed");
         std::vector<PlScanDev> h(n);
         for (size_t i = 0; i < n; i++) {
@@ -697,16 +698,17 @@ extern "C" int pngloss_b200_batch_scanlines(pngloss_b200_batch *b) {
     PL_CUDA(ctx, cudaEventRecord(b->ev_scan[0], b->stream));
     pl_k4_scan_output<<<(unsigned)(n * slices), PL_K4_THREADS, 0, b->stream>>>(b->dscan, slices);
     PL_CUDA(ctx, cudaGetLastError());
+    PL_CUDA(ctx, cudaEventRecord(b->ev_scan[1], b->stream));
     pl_k4_scanlines<<<(unsigned)(n * slices), PL_K4_THREADS, 0, b->stream>>>(b->dscan, slices);
     PL_CUDA(ctx, cudaGetLastError());
-    PL_CUDA(ctx, cudaEventRecord(b->ev_scan[1], b->stream));
+    PL_CUDA(ctx, cudaEventRecord(b->ev_scan[2], b->stream));
     PL_CUDA(ctx, cudaMemcpyAsync(b->hoflags, b->oflags, n * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
     b->scan_ran = true;
     return PNGLOSS_B200_SUCCESS;
 }
 
 extern "C" int pngloss_b200_batch_scanline_info(pngloss_b200_batch *b, size_t i, uint32_t *bytes_per_pixel,
-                                                uint32_t *row0_filter, size_t *bytes, float *milliseconds) {
+                                                uint32_t *row0_filter, size_t *bytes, float milliseconds[2]) {
     if (!b || i >= b->n || !b->scan_ran) return PNGLOSS_B200_INVALID_ARGUMENT;
     pngloss_b200_ctx *ctx = b->ctx;
     PL_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -716,7 +718,10 @@ extern "C" int pngloss_b200_batch_scanline_info(pngloss_b200_batch *b, size_t i,
     if (bytes_per_pixel) *bytes_per_pixel = bpp;
     if (row0_filter) *row0_filter = f[2];
     if (bytes) *bytes = (size_t)b->h[i] * (1 + (size_t)b->w[i] * bpp);
-    if (milliseconds) PL_CUDA(ctx, cudaEventElapsedTime(milliseconds, b->ev_scan[0], b->ev_scan[1]));
+    if (milliseconds) {
+        PL_CUDA(ctx, cudaEventElapsedTime(&milliseconds[0], b->ev_scan[0], b->ev_scan[1]));
+        PL_CUDA(ctx, cudaEventElapsedTime(&milliseconds[1], b->ev_scan[1], b->ev_scan[2]));
+    }
     return PNGLOSS_B200_SUCCESS;
 }
 

@@ -1127,11 +1127,40 @@ __global__ void __launch_bounds__(PL_K4_THREADS) pl_k4_scan_output(const PlScanD
     const PlScanDev im = imgs[blockIdx.x / slices];
     const size_t n = (size_t)im.width * im.height;
     unsigned notgray = 0, notopaque = 0;
-    for (size_t i = (size_t)(blockIdx.x % slices) * PL_K4_THREADS + threadIdx.x; i < n;
-         i += (size_t)slices * PL_K4_THREADS) {
-        const uchar4 p = im.px[i];
-        notgray |= (unsigned)(p.x != p.y || p.y != p.z);
-        notopaque |= (unsigned)(p.w < 255);
+    const size_t first = (size_t)(blockIdx.x % slices) * PL_K4_THREADS + threadIdx.x;
+    const size_t step = (size_t)slices * PL_K4_THREADS;
+    // four pixels per load, four loads in flight per thread (the image buffers are 256-byte aligned)
+    const uint4 *p4 = (const uint4 *)im.px;
+    const size_t n4 = n / 4;
+    size_t i = first;
+    for (; i + 3 * step < n4; i += 4 * step) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = p4[i + u * step];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const unsigned w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                // gray: R == G == B, i.e. the word equals itself with G copied over R and B
+                notgray |= (unsigned)(__byte_perm(w[k], 0u, 0x3111u) != w[k]);
+                notopaque |= (unsigned)(w[k] < 0xff000000u);
+            }
+        }
+    }
+    for (; i < n4; i += step) {
+        const uint4 v = p4[i];
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            notgray |= (unsigned)(__byte_perm(w[k], 0u, 0x3111u) != w[k]);
+            notopaque |= (unsigned)(w[k] < 0xff000000u);
+        }
+    }
+    for (size_t j = n4 * 4 + first; j < n; j += step) {   // the last n % 4 pixels
+        const unsigned w = pl_u32(im.px[j]);
+        notgray |= (unsigned)(__byte_perm(w, 0u, 0x3111u) != w);
+        notopaque |= (unsigned)(w < 0xff000000u);
     }
     if (__any_sync(PL_FULL, notgray) && (threadIdx.x & 31) == 0) atomicOr(&im.oflags[0], 1u);
     if (__any_sync(PL_FULL, notopaque) && (threadIdx.x & 31) == 0) atomicOr(&im.oflags[1], 1u);
@@ -1139,7 +1168,8 @@ __global__ void __launch_bounds__(PL_K4_THREADS) pl_k4_scan_output(const PlScanD
 
 // bytes of a pixel in the narrowed layout: byte selector for __byte_perm (gray: G; gray+alpha: G,A; ...)
 __device__ __forceinline__ unsigned pl_k4_narrow(unsigned rgba, int bpp) {
-    return bpp == 1 ? __byte_perm(rgba, 0u, 0x4441u) : bpp == 2 ? __byte_perm(rgba, 0u, 0x4431u) : rgba;
+    return bpp == 1 ? __byte_perm(rgba, 0u, 0x4441u) : bpp == 2 ? __byte_perm(rgba, 0u, 0x4431u)
+           : bpp == 3 ? rgba & 0x00ffffffu : rgba;   // bytes beyond bpp are zero
 }
 // the bpp filtered bytes of one pixel, packed into the low bytes of a word
 __device__ __forceinline__ unsigned pl_k4_filter_pixel(int type, int bpp, unsigned cur, unsigned left, unsigned up,
@@ -1156,64 +1186,215 @@ __device__ __forceinline__ unsigned pl_k4_filter_pixel(int type, int bpp, unsign
     return r;
 }
 
-__global__ void __launch_bounds__(PL_K4_THREADS) pl_k4_scanlines(const PlScanDev *imgs, unsigned slices) {
-    // staging of one segment: up to 256 pixels * 4 bytes, shifted by the misalignment of its destination
-    __shared__ __align__(16) unsigned char stage[PL_K4_THREADS * 4 + 8];
+// The same for all four bytes of a word at once (bytes the colour type does not use are zero in every
+// operand and stay zero): per-byte subtraction modulo 256 and the per-byte floor average.
+__device__ __forceinline__ unsigned pl_bytes_sub(unsigned a, unsigned b) {
+    // keep the borrow of each byte inside that byte
+    return ((a | 0x80808080u) - (b & 0x7f7f7f7fu)) ^ ((a ^ ~b) & 0x80808080u);
+}
+__device__ __forceinline__ unsigned pl_bytes_avg(unsigned a, unsigned b) {
+    return (a & b) + (((a ^ b) & 0xfefefefeu) >> 1);
+}
+__device__ __forceinline__ unsigned pl_k4_filter_word(int type, int bpp, unsigned cur, unsigned left, unsigned up,
+                                                      unsigned ul) {
+    if (type == 4) return pl_k4_filter_pixel(4, bpp, cur, left, up, ul);
+    const unsigned pred = type == 1 ? left : type == 2 ? up : type == 3 ? pl_bytes_avg(left, up) : 0u;
+    return pl_bytes_sub(cur, pred);
+}
+
+// filter type of row y: row 0 by the heuristic (row0_type), the others from K2's libpng masks
+__device__ __forceinline__ int pl_k4_row_type(const PlScanDev &im, int y, int row0_type) {
+    if (y == 0) return row0_type;
+    const unsigned m = im.filters[y];
+    return m == 0x10 ? 1 : m == 0x20 ? 2 : m == 0x40 ? 3 : m == 0x80 ? 4 : 0;
+}
+
+// Vector path of K4 (width a multiple of 4, so rows are 16-byte aligned): the CTA's rows are cut into
+// segments of 1024 pixels; a thread takes four pixels of a segment = 4 * bpp bytes = bpp whole words of the
+// output stream, which are staged as words; the copy-out realigns the stream to the destination with funnel
+// shifts and writes 16-byte vectors.  The loads of segment s + 1 are issued before segment s is copied out and
+// the stage is double buffered, so there is one barrier per segment and loads are always in flight.
+#define PL_K4_PX 4
+#define PL_K4_STAGE_WORDS (PL_K4_THREADS * PL_K4_PX + 8)
+struct PlK4Seg {
+    uint4 c4, u4;        // four pixels of the row and of the row above
+    unsigned left, ul;   // the pixel before them, narrowed
+};
+// four pixels' worth of filtered bytes: the filter type is the same for the whole CTA, so the switch is uniform
+template <int BPP, int TYPE>
+__device__ __forceinline__ void pl_k4_filter4(const PlK4Seg &g, unsigned (&r)[4]) {
+    const unsigned cw[4] = {g.c4.x, g.c4.y, g.c4.z, g.c4.w}, uw[4] = {g.u4.x, g.u4.y, g.u4.z, g.u4.w};
+    unsigned left = g.left, ul = g.ul;
+#pragma unroll
+    for (int k = 0; k < PL_K4_PX; k++) {
+        const unsigned cur = pl_k4_narrow(cw[k], BPP), up = pl_k4_narrow(uw[k], BPP);
+        r[k] = pl_k4_filter_word(TYPE, BPP, cur, left, up, ul);
+        left = cur;
+        ul = up;
+    }
+}
+template <int BPP>
+__device__ __forceinline__ void pl_k4_vector_rows(const PlScanDev &im, int first_row, int slices, int row0_type,
+                                                  unsigned (*stage)[PL_K4_STAGE_WORDS]) {
+    const int W = (int)im.width, H = (int)im.height, tid = threadIdx.x;
+    const size_t stride = 1 + (size_t)W * BPP;
+    const int seg_px = PL_K4_THREADS * PL_K4_PX;
+    auto load = [&](int y, int x0, PlK4Seg &g) {
+        const int x = x0 + tid * PL_K4_PX;
+        if (y < H && x < W) {
+            const uchar4 *row = im.px + (size_t)y * W;
+            g.c4 = *(const uint4 *)(row + x);
+            g.left = x ? pl_k4_narrow(pl_u32(row[x - 1]), BPP) : 0u;
+            g.u4 = make_uint4(0u, 0u, 0u, 0u);
+            g.ul = 0u;
+            if (y) {
+                g.u4 = *(const uint4 *)(row - W + x);
+                g.ul = x ? pl_k4_narrow(pl_u32(row[x - 1 - W]), BPP) : 0u;
+            }
+        }
+    };
+    PlK4Seg seg;
+    load(first_row, 0, seg);
+    int buf = 0;
+    for (int y = first_row, x0 = 0; y < H; buf ^= 1) {
+        const int type = pl_k4_row_type(im, y, row0_type);
+        const int npx = min(seg_px, W - x0), len = npx * BPP;       // pixels and bytes of this segment
+        unsigned *stage_w = stage[buf];
+        unsigned char *dst_row = im.scan + (size_t)y * stride;
+        if (x0 == 0 && tid == 0) dst_row[0] = (unsigned char)type;
+        if (tid * PL_K4_PX < npx) {
+            unsigned r[4];
+            switch (type) {
+            case 0: pl_k4_filter4<BPP, 0>(seg, r); break;
+            case 1: pl_k4_filter4<BPP, 1>(seg, r); break;
+            case 2: pl_k4_filter4<BPP, 2>(seg, r); break;
+            case 3: pl_k4_filter4<BPP, 3>(seg, r); break;
+            default: pl_k4_filter4<BPP, 4>(seg, r); break;
+            }
+            unsigned *sp = stage_w + tid * BPP;
+            if (BPP == 4) {
+                *(uint4 *)sp = make_uint4(r[0], r[1], r[2], r[3]);
+            } else if (BPP == 3) {
+                sp[0] = r[0] | (r[1] << 24);
+                sp[1] = (r[1] >> 8) | (r[2] << 16);
+                sp[2] = (r[2] >> 16) | (r[3] << 8);
+            } else if (BPP == 2) {
+                sp[0] = r[0] | (r[1] << 16);
+                sp[1] = r[2] | (r[3] << 16);
+            } else {
+                sp[0] = r[0] | (r[1] << 8) | (r[2] << 16) | (r[3] << 24);
+            }
+        }
+        if (tid == 0) stage_w[len >> 2] = 0u;   // the word after the stream (read by the last shift)
+        // next segment: its loads are in flight during the barrier and the copy-out
+        unsigned char *g0 = dst_row + 1 + (size_t)x0 * BPP;
+        x0 += seg_px;
+        if (x0 >= W) {
+            x0 = 0;
+            y += slices;
+        }
+        load(y, x0, seg);
+        __syncthreads();
+        // 16-byte vectors of the destination [g0 - mis, g0 + len): vector v holds stream bytes
+        // 16 v - mis .. 16 v - mis + 15
+        const int mis = (int)((size_t)g0 & 15u);
+        const int nvec = (mis + len + 15) >> 4;
+        const int sh = ((16 - mis) & 3) * 8;                        // stream word -> destination word shift
+        const unsigned char *sb = (const unsigned char *)stage_w;
+        for (int vi = tid; vi < nvec; vi += PL_K4_THREADS) {
+            const int o = vi * 16 - mis;                            // stream offset of the vector's first byte
+            if (o >= 0 && o + 16 <= len) {
+                const unsigned *q = stage_w + (o >> 2);
+                const unsigned w0 = q[0], w1 = q[1], w2 = q[2], w3 = q[3], w4 = q[4];
+                *(uint4 *)(g0 + o) = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh),
+                                                __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+            }
+        }
+        // the ragged first and last vector, one byte per thread
+        if (tid < 32) {
+            const int o = (tid < 16 ? 0 : (nvec - 1) * 16) - mis + (tid & 15);
+            const bool ragged = tid < 16 ? mis != 0 : (nvec > 1 && ((mis + len) & 15) != 0);
+            if (ragged && o >= 0 && o < len) g0[o] = sb[o];
+        }
+        // no second barrier: the next segment is staged in the other buffer, and the one after that only after
+        // the next barrier, which every thread reaches after this copy-out
+    }
+}
+
+#ifndef PL_K4_MIN_BLOCKS
+#define PL_K4_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(PL_K4_THREADS, PL_K4_MIN_BLOCKS)
+pl_k4_scanlines(const PlScanDev *imgs, unsigned slices) {
+    // staging of a segment of the output stream, double buffered (vector path) / byte stage (scalar path)
+    __shared__ __align__(16) unsigned stage2[2][PL_K4_STAGE_WORDS];
     __shared__ unsigned red[5][PL_K4_THREADS / 32];
-    __shared__ int row0_type;
+    __shared__ int row0_type_s;
+    unsigned char *stage = (unsigned char *)stage2[0];
     const PlScanDev im = imgs[blockIdx.x / slices];
     const int W = (int)im.width, H = (int)im.height;
     const bool gray = im.oflags[0] == 0, opaque = im.oflags[1] == 0;
     const int bpp = gray ? (opaque ? 1 : 2) : (opaque ? 3 : 4);
     const size_t stride = 1 + (size_t)W * bpp;
     const int tid = threadIdx.x;
+    const int first_row = (int)(blockIdx.x % slices);
 
-    for (int y = (int)(blockIdx.x % slices); y < H; y += (int)slices) {
-        const uchar4 *row = im.px + (size_t)y * W;
-        const uchar4 *above = row - W;   // only read when y > 0
-        int type;
-        if (y == 0) {
-            // libpng's heuristic on row 0 (reference src/rwpng.c:488-495 leaves it to libpng): the filter
-            // with the smallest sum of |signed residual|, first minimum in the order none .. paeth
-            unsigned sum[5] = {0, 0, 0, 0, 0};
-            for (int x = tid; x < W; x += PL_K4_THREADS) {
-                const unsigned cur = pl_k4_narrow(pl_u32(row[x]), bpp);
-                const unsigned left = x ? pl_k4_narrow(pl_u32(row[x - 1]), bpp) : 0u;
-#pragma unroll
-                for (int f = 0; f < 5; f++) {
-                    const unsigned r = pl_k4_filter_pixel(f, bpp, cur, left, 0u, 0u);
-#pragma unroll
-                    for (int c = 0; c < 4; c++)
-                        if (c < bpp) {
-                            const unsigned v = (r >> (8 * c)) & 255u;
-                            sum[f] += v < 128u ? v : 256u - v;
-                        }
-                }
-            }
+    int row0_type = 0;
+    if (first_row == 0) {
+        // libpng's heuristic on row 0 (reference src/rwpng.c:488-495 leaves it to libpng): the filter
+        // with the smallest sum of |signed residual|, first minimum in the order none .. paeth
+        const uchar4 *row = im.px;
+        unsigned sum[5] = {0, 0, 0, 0, 0};
+        for (int x = tid; x < W; x += PL_K4_THREADS) {
+            const unsigned cur = pl_k4_narrow(pl_u32(row[x]), bpp);
+            const unsigned left = x ? pl_k4_narrow(pl_u32(row[x - 1]), bpp) : 0u;
 #pragma unroll
             for (int f = 0; f < 5; f++) {
+                const unsigned r = pl_k4_filter_pixel(f, bpp, cur, left, 0u, 0u);
 #pragma unroll
-                for (int mk = 16; mk >= 1; mk >>= 1) sum[f] += __shfl_xor_sync(PL_FULL, sum[f], mk);
-                if ((tid & 31) == 0) red[f][tid >> 5] = sum[f];
+                for (int c = 0; c < 4; c++)
+                    if (c < bpp) {
+                        const unsigned v = (r >> (8 * c)) & 255u;
+                        sum[f] += v < 128u ? v : 256u - v;
+                    }
             }
-            __syncthreads();
-            if (tid == 0) {
-                unsigned best = ~0u;
-                int pick = 0;
-                for (int f = 0; f < 5; f++) {
-                    unsigned t = 0;
-                    for (int k = 0; k < PL_K4_THREADS / 32; k++) t += red[f][k];
-                    if (t < best) { best = t; pick = f; }
-                }
-                row0_type = pick;
-                im.oflags[2] = (unsigned)pick;
-            }
-            __syncthreads();
-            type = row0_type;
-        } else {
-            const unsigned m = im.filters[y];
-            type = m == 0x10 ? 1 : m == 0x20 ? 2 : m == 0x40 ? 3 : m == 0x80 ? 4 : 0;
         }
+#pragma unroll
+        for (int f = 0; f < 5; f++) {
+#pragma unroll
+            for (int mk = 16; mk >= 1; mk >>= 1) sum[f] += __shfl_xor_sync(PL_FULL, sum[f], mk);
+            if ((tid & 31) == 0) red[f][tid >> 5] = sum[f];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned best = ~0u;
+            int pick = 0;
+            for (int f = 0; f < 5; f++) {
+                unsigned t = 0;
+                for (int k = 0; k < PL_K4_THREADS / 32; k++) t += red[f][k];
+                if (t < best) { best = t; pick = f; }
+            }
+            row0_type_s = pick;
+            im.oflags[2] = (unsigned)pick;
+        }
+        __syncthreads();
+        row0_type = row0_type_s;
+    }
+
+    if ((W & 3) == 0) {
+        switch (bpp) {
+        case 1: pl_k4_vector_rows<1>(im, first_row, (int)slices, row0_type, stage2); break;
+        case 2: pl_k4_vector_rows<2>(im, first_row, (int)slices, row0_type, stage2); break;
+        case 3: pl_k4_vector_rows<3>(im, first_row, (int)slices, row0_type, stage2); break;
+        default: pl_k4_vector_rows<4>(im, first_row, (int)slices, row0_type, stage2); break;
+        }
+        return;
+    }
+    // scalar path: one pixel per thread, bytes staged at the destination's misalignment, 4-byte words out
+    for (int y = first_row; y < H; y += (int)slices) {
+        const uchar4 *row = im.px + (size_t)y * W;
+        const uchar4 *above = row - W;   // only read when y > 0
+        const int type = pl_k4_row_type(im, y, row0_type);
         unsigned char *dst_row = im.scan + (size_t)y * stride;
         if (tid == 0) dst_row[0] = (unsigned char)type;
         for (int x0 = 0; x0 < W; x0 += PL_K4_THREADS) {

@@ -222,6 +222,9 @@ template <class T> static inline T atomicExch(T *p, T v) { T o = *p; *p = v; ret
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) {
+    return (unsigned)((((unsigned long long)hi << 32) | lo) >> (sh & 31));
+}
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) {
     unsigned long long src = ((unsigned long long)b << 32) | a;

@@ -164,7 +164,7 @@ def test_emu_k4_scanlines(emu, oracle):
     scanlines - against a numpy restatement of the PNG filters, and through a real PNG decoder."""
     from PIL import Image
     rng = np.random.default_rng(21)
-    for (w, h) in [(37, 9), (1, 5), (300, 4), (256, 3), (5, 1)]:
+    for (w, h) in [(37, 9), (1, 5), (300, 4), (256, 3), (5, 1), (2052, 3), (1028, 2)]:
         for bpp in (1, 2, 3, 4):
             src = to_bpp(oracle.synth(w, h, 60 + bpp), bpp) if w > 1 else \
                 to_bpp(rng.integers(0, 256, (h, w, 4), dtype=np.uint8), bpp)
