@@ -1321,11 +1321,7 @@ __device__ __forceinline__ void pl_k4_vector_rows(const PlScanDev &im, int first
     }
 }
 
-#ifndef PL_K4_MIN_BLOCKS
-#define PL_K4_MIN_BLOCKS 1
-#endif
-__global__ void __launch_bounds__(PL_K4_THREADS, PL_K4_MIN_BLOCKS)
-pl_k4_scanlines(const PlScanDev *imgs, unsigned slices) {
+__global__ void __launch_bounds__(PL_K4_THREADS) pl_k4_scanlines(const PlScanDev *imgs, unsigned slices) {
     // staging of a segment of the output stream, double buffered (vector path) / byte stage (scalar path)
     __shared__ __align__(16) unsigned stage2[2][PL_K4_STAGE_WORDS];
     __shared__ unsigned red[5][PL_K4_THREADS / 32];
