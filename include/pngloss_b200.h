@@ -102,7 +102,15 @@ typedef struct {
     int status;                 /* out: PNGLOSS_B200_* for this image */
     unsigned char *out_pixels;  /* NULL: quantise `pixels` in place; else the result goes here and */
     size_t out_stride;          /* `pixels` is left alone */
+    /* Optional: the result as filtered PNG scanlines, ready for deflate (see pngloss_b200_batch_scanlines).
+     * scanlines: NULL, or room for height * (1 + 4 * width) bytes. */
+    unsigned char *scanlines;
+    uint32_t flags;             /* PNGLOSS_B200_IMAGE_* */
+    uint32_t scan_bytes_per_pixel; /* out: 1 gray, 2 gray+alpha, 3 rgb, 4 rgba - what the output pixels allow */
+    uint32_t scan_row0_filter;  /* out: PNG filter type libpng's heuristic picks for row 0 */
+    size_t scan_bytes;          /* out: height * (1 + width * scan_bytes_per_pixel) */
 } pngloss_b200_image;
+#define PNGLOSS_B200_IMAGE_NO_PIXELS 1u   /* with `scanlines`: do not copy the quantised pixels back */
 
 /* Upload, run, download a batch of independent images.  Blocking.  Returns the first non-zero
  * per-image status, or 0.  A batch that does not fit the device runs as consecutive groups whose

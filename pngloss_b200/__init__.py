@@ -60,7 +60,10 @@ class ImageDesc(ctypes.Structure):
                 ("width", ctypes.c_uint32), ("height", ctypes.c_uint32),
                 ("row_filters", ctypes.c_void_p), ("force_bytes_per_pixel", ctypes.c_uint32),
                 ("bytes_per_pixel", ctypes.c_uint32), ("retried_rows", ctypes.c_uint32),
-                ("status", ctypes.c_int), ("out_pixels", ctypes.c_void_p), ("out_stride", ctypes.c_size_t)]
+                ("status", ctypes.c_int), ("out_pixels", ctypes.c_void_p), ("out_stride", ctypes.c_size_t),
+                ("scanlines", ctypes.c_void_p), ("flags", ctypes.c_uint32),
+                ("scan_bytes_per_pixel", ctypes.c_uint32), ("scan_row0_filter", ctypes.c_uint32),
+                ("scan_bytes", ctypes.c_size_t)]
 
 
 _lib = None
@@ -235,7 +238,7 @@ class Context:
         lib.pngloss_b200_host_free(p)
 
     @staticmethod
-    def _descs(images, row_filters, force_bpp, outputs=None):
+    def _descs(images, row_filters, force_bpp, outputs=None, scanlines=None, no_pixels=False):
         n = len(images)
         descs = (ImageDesc * n)()
         for i, a in enumerate(images):
@@ -252,20 +255,27 @@ class Context:
                 assert o.dtype == np.uint8 and o.shape == a.shape and o.strides[1] == 4
                 descs[i].out_pixels = o.ctypes.data
                 descs[i].out_stride = o.strides[0]
+            if scanlines is not None:
+                sc = scanlines[i]
+                assert sc.dtype == np.uint8 and sc.size >= a.shape[0] * (1 + 4 * a.shape[1])
+                descs[i].scanlines = sc.ctypes.data
+                descs[i].flags = 1 if no_pixels else 0
         return descs
 
     def optimize_batch(self, images: Sequence[np.ndarray],
                        row_filters: Optional[Sequence[Optional[np.ndarray]]], strength: int,
                        bleed: int, force_bpp: int = 0,
-                       outputs: Optional[Sequence[np.ndarray]] = None) -> List[dict]:
+                       outputs: Optional[Sequence[np.ndarray]] = None,
+                       scanlines: Optional[Sequence[np.ndarray]] = None, no_pixels: bool = False) -> List[dict]:
         """Host-buffer batch: images are quantised in place (or into `outputs`).  row_filters: list of
         (h,) uint8 arrays, entries (or the list) may be None for the reference's row_filters == NULL
         semantics."""
-        descs = self._descs(images, row_filters, force_bpp, outputs)
+        descs = self._descs(images, row_filters, force_bpp, outputs, scanlines, no_pixels)
         rc = self.lib.pngloss_b200_optimize_batch(self.handle, descs, len(images), strength, bleed)
         self._check(rc)
-        return [dict(status=d.status, bytes_per_pixel=d.bytes_per_pixel, retried_rows=d.retried_rows)
-                for d in descs]
+        return [dict(status=d.status, bytes_per_pixel=d.bytes_per_pixel, retried_rows=d.retried_rows,
+                     scan_bytes_per_pixel=d.scan_bytes_per_pixel, scan_row0_filter=d.scan_row0_filter,
+                     scan_bytes=d.scan_bytes) for d in descs]
 
     def submit(self, images, row_filters, strength: int, bleed: int, force_bpp: int = 0, outputs=None) -> "Job":
         """Asynchronous optimize_batch (pngloss_b200_submit): returns a Job; Job.wait() blocks and returns

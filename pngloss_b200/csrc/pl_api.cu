@@ -76,6 +76,7 @@ struct pngloss_b200_job {
     pngloss_b200_image *images = nullptr;
     size_t n = 0;
     bool finalized = false;
+    bool scanlines = false;   // some image asked for filtered scanlines (K4 ran)
     int rc = 0;
 };
 
@@ -738,9 +739,10 @@ extern "C" int pngloss_b200_batch_download_scanlines(pngloss_b200_batch *b, size
 }
 
 // Upper bound of what an in-place batch allocates for one image (see the slab layout in batch_create_ex).
-static size_t device_bytes_per_image(uint32_t w, uint32_t h) {
+static size_t device_bytes_per_image(uint32_t w, uint32_t h, bool scanlines) {
     const size_t px = (size_t)w * h;
-    return align_up(px * 4, 256) + align_up((size_t)w * 4, 256) + align_up(h, 16) +
+    return (scanlines ? align_up((size_t)h * (1 + (size_t)w * 4), 256) + sizeof(PlScanDev) + 16 : 0) +
+           align_up(px * 4, 256) + align_up((size_t)w * 4, 256) + align_up(h, 16) +
            align_up((size_t)2 * PL_FILTERS * 2 * (w + PL_ERR_PAD) * sizeof(short4), 256) +
            align_up((size_t)PL_FILTERS * w * 4, 256) + PL_FILTERS * 4 * 256 * sizeof(uint32_t) +
            256 * sizeof(uint32_t) + sizeof(PlImageDev) + 8 * sizeof(int) + 64 + 1024;
@@ -774,6 +776,24 @@ static int finalize_job(pngloss_b200_job *job) {
                 memcpy(job->images[i].row_filters, b->hfilters + b->filt_off[i], b->h[i]);
             if (st && !first)
                 first = set_err(ctx, st, "image %zu: no acceptable row even at strength 0", i);
+        }
+        if (job->scanlines) {
+            // the colour types are known now: fetch exactly the bytes each image's scanlines take
+            for (size_t i = 0; i < job->n && e == cudaSuccess; i++) {
+                pngloss_b200_image &im = job->images[i];
+                if (!im.scanlines) continue;
+                const uint32_t *f = b->hoflags + i * 4;
+                im.scan_bytes_per_pixel = f[0] ? (f[1] ? 4u : 3u) : (f[1] ? 2u : 1u);
+                im.scan_row0_filter = f[2];
+                im.scan_bytes = (size_t)b->h[i] * (1 + (size_t)b->w[i] * im.scan_bytes_per_pixel);
+                e = cudaMemcpyAsync(im.scanlines, b->scan_slab + b->scan_off[i], im.scan_bytes,
+                                    cudaMemcpyDeviceToHost, ctx->d2h);
+            }
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->d2h);
+            if (e != cudaSuccess) {
+                first = set_err(ctx, PNGLOSS_B200_DEVICE_ERROR, "scanline download failed: %s", cudaGetErrorString(e));
+                for (size_t i = 0; i < job->n; i++) job->images[i].status = first;
+            }
         }
     }
     b->busy = false;
@@ -894,6 +914,11 @@ extern "C" int pngloss_b200_submit(pngloss_b200_ctx *ctx, pngloss_b200_image *im
     // compute stream: kernels, then the per-image status words
     if (!rc && e == cudaSuccess) e = cudaStreamWaitEvent(b->stream, b->ev_up, 0);
     if (!rc && e == cudaSuccess) rc = launch_run(b, strength, bleed, lpc, nblocks);
+    for (size_t i = 0; i < n; i++) job->scanlines |= images[i].scanlines != nullptr;
+    if (!rc && e == cudaSuccess && job->scanlines) {
+        b->ran = true;
+        rc = pngloss_b200_batch_scanlines(b);   // K4 on the compute stream; flags come back with it
+    }
     if (!rc && e == cudaSuccess)
         e = cudaMemcpyAsync(b->hstatus, b->status, b->n * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                             b->stream);
@@ -904,10 +929,12 @@ extern "C" int pngloss_b200_submit(pngloss_b200_ctx *ctx, pngloss_b200_image *im
     // travel through a pinned staging buffer and reach the caller's arrays in pngloss_b200_wait)
     auto dst_of = [&](size_t i) { return images[i].out_pixels ? images[i].out_pixels : images[i].pixels; };
     auto dstride_of = [&](size_t i) { return images[i].out_pixels ? images[i].out_stride : images[i].stride; };
+    auto skip_px = [&](size_t i) { return images[i].scanlines && (images[i].flags & PNGLOSS_B200_IMAGE_NO_PIXELS); };
     for (size_t i = 0; i < n && !rc && e == cudaSuccess;) {
+        if (skip_px(i)) { i++; continue; }
         size_t e2 = i + 1, bytes = (size_t)b->w[i] * b->h[i] * 4;
         if (dstride_of(i) == (size_t)b->w[i] * 4) {
-            while (e2 < n && dstride_of(e2) == (size_t)b->w[e2] * 4 && dst_of(e2) == dst_of(i) + bytes &&
+            while (e2 < n && !skip_px(e2) && dstride_of(e2) == (size_t)b->w[e2] * 4 && dst_of(e2) == dst_of(i) + bytes &&
                    (const unsigned char *)b->himgs[e2].out == (const unsigned char *)b->himgs[i].out + bytes) {
                 bytes += (size_t)b->w[e2] * b->h[e2] * 4;
                 e2++;
@@ -965,7 +992,8 @@ extern "C" int pngloss_b200_optimize_batch(pngloss_b200_ctx *ctx, pngloss_b200_i
     if (const char *e = getenv("PNGLOSS_B200_MEM_BUDGET_MB"))   // tests: force the grouping on small inputs
         budget = std::min(budget, (size_t)strtoull(e, nullptr, 10) << 20);
     size_t need_all = 0;
-    for (size_t i = 0; i < n; i++) need_all += device_bytes_per_image(images[i].width, images[i].height);
+    for (size_t i = 0; i < n; i++)
+        need_all += device_bytes_per_image(images[i].width, images[i].height, images[i].scanlines != nullptr);
     // everything at once if it fits; otherwise groups of half the budget, two in flight, so that the
     // copies of one group hide behind the kernels of the other
     const bool grouped = need_all > budget;
@@ -975,7 +1003,8 @@ extern "C" int pngloss_b200_optimize_batch(pngloss_b200_ctx *ctx, pngloss_b200_i
     for (size_t begin = 0; begin < n;) {
         size_t end = begin, need = 0;
         while (end < n) {
-            const size_t one = device_bytes_per_image(images[end].width, images[end].height);
+            const size_t one = device_bytes_per_image(images[end].width, images[end].height,
+                                                      images[end].scanlines != nullptr);
             if (end > begin && need + one > budget) break;
             need += one;
             end++;

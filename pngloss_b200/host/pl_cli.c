@@ -178,6 +178,10 @@ struct job {
     char *outname, *outname_free;
     png24_image input, output;
     unsigned char *row_filters;
+    /* the result as filtered scanlines from the GPU (K4); NULL with PNGLOSS_CPU_FILTER=1, then the writer narrows
+     * and filters the quantised pixels itself like the reference's libpng does */
+    unsigned char *scanlines;
+    unsigned scan_bpp;
     pngloss_error rc;
     bool loaded;
     char *log;          /* this file's messages, printed in file order once a phase is over */
@@ -222,8 +226,8 @@ static pngloss_error prepare_output_image(const png24_image *in, png24_image *ou
 }
 
 /* reference src/pngloss.c:375-431: temp file + rename so that a failed write never damages the target */
-static pngloss_error write_image(png24_image *img, unsigned char *row_filters, const char *outname,
-                                 const struct options *o, FILE *log) {
+static pngloss_error write_image(png24_image *img, unsigned char *row_filters, const unsigned char *scanlines,
+                                 unsigned scan_bpp, const char *outname, const struct options *o, FILE *log) {
     FILE *out;
     char *tempname = NULL;
     if (o->using_stdout) {
@@ -240,7 +244,8 @@ static pngloss_error write_image(png24_image *img, unsigned char *row_filters, c
         }
         if (o->verbose) fprintf(log, "  writing compressed image as %s\n", filename_part(outname));
     }
-    pngloss_error rc = rwpng_write_image24(out, img, row_filters);
+    pngloss_error rc = scanlines ? rwpng_write_scanlines(out, img, scan_bpp, scanlines)
+                                 : rwpng_write_image24(out, img, row_filters);
     if (!o->using_stdout) {
         fclose(out);
         if (rc == SUCCESS && rename(tempname, outname) != 0) rc = CANT_WRITE_ERROR;
@@ -333,6 +338,8 @@ static void decode_job(struct run *r, unsigned i) {
     }
     j->rc = prepare_output_image(&j->input, &j->output);
     j->row_filters = malloc(j->input.height);   /* NULL is a valid value (reference :262-263) */
+    if (!getenv("PNGLOSS_CPU_FILTER"))          /* NULL is a valid value here too: CPU filtering */
+        j->scanlines = malloc((size_t)j->input.height * (1 + 4 * (size_t)j->input.width));
     if (!j->rc) j->loaded = true;
 }
 
@@ -344,7 +351,7 @@ static void encode_job(struct run *r, unsigned i) {
     if (o->skip_if_larger) j->output.maximum_file_size = j->input.file_size - 1;
     j->output.chunks = j->input.chunks;
     j->input.chunks = NULL;
-    j->rc = write_image(&j->output, j->row_filters, j->outname, o, j->logf);
+    j->rc = write_image(&j->output, j->row_filters, j->scanlines, j->scan_bpp, j->outname, o, j->logf);
     if (o->verbose) {
         if (j->rc == SUCCESS) {
             fprintf(j->logf, "  wrote %luKB file (%.1f%% of original)\n",
@@ -360,7 +367,7 @@ static void encode_job(struct run *r, unsigned i) {
     }
     /* on stdout an empty result would be nasty: send the original instead (reference :286-293) */
     if (o->using_stdout && j->rc == TOO_LARGE_FILE) {
-        pngloss_error wrc = write_image(&j->input, NULL, j->outname, o, j->logf);
+        pngloss_error wrc = write_image(&j->input, NULL, NULL, 0, j->outname, o, j->logf);
         if (wrc) j->rc = wrc;
     }
 }
@@ -422,6 +429,8 @@ static void run_gpus(struct run *r) {
         all[k].im.width = j->output.width;
         all[k].im.height = j->output.height;
         all[k].im.row_filters = j->row_filters;
+        all[k].im.scanlines = j->scanlines;
+        all[k].im.flags = j->scanlines ? PNGLOSS_B200_IMAGE_NO_PIXELS : 0;   /* the encoder needs nothing else */
         all[k].job = i;
         k++;
     }
@@ -461,6 +470,7 @@ static void run_gpus(struct run *r) {
                 fprintf(stderr, "\naborting because no good row in %s\n", j->filename);   /* reference abort()s */
                 abort();
             }
+            j->scan_bpp = s->images[q].scan_bytes_per_pixel;
             if (st) j->rc = st == PNGLOSS_B200_OUT_OF_MEMORY ? OUT_OF_MEMORY_ERROR : PNGLOSS_DEVICE_ERROR;
             else if (o->verbose)
                 fprintf(j->logf, "%s:\n  compression complete (%u bytes per pixel, GPU %d)\n", j->filename,
@@ -537,6 +547,7 @@ int main(int argc, char *argv[]) {
         rwpng_free_image24(&j->input);
         rwpng_free_image24(&j->output);
         free(j->row_filters);
+        free(j->scanlines);
         free(j->outname_free);
         if (j->logf && j->logf != stderr) fclose(j->logf);
         free(j->log);

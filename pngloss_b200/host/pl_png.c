@@ -430,30 +430,20 @@ static void write_passthrough(sink *s, png24_image *img, int location) {
 
 #define IDAT_BYTES 8192   /* libpng's default compression buffer: one IDAT chunk per 8 KB of deflate output */
 
-pngloss_error rwpng_write_image24(FILE *outfile, png24_image *img, unsigned char *row_filters) {
+/* The container around a stream of filtered scanlines: signature, IHDR, colour tags, passed-through chunks,
+ * IDAT (zlib level 9, memLevel 9 - reference src/rwpng.c:471-472 - with the filtered-data strategy and a
+ * window no larger than the data needs, 8 KB chunks), IEND.  next_row(ctx, y) returns row y: one filter-type
+ * byte and width * bpp filtered bytes. */
+typedef const unsigned char *(*row_source)(void *ctx, uint32_t y);
+
+static pngloss_error write_png_stream(FILE *outfile, png24_image *img, unsigned bpp, row_source next_row, void *ctx) {
     const uint32_t w = img->width, h = img->height;
     sink s = {outfile, 0, img->maximum_file_size, SUCCESS};
     img->metadata_size = 0;
-
-    /* autodetect grayscale and alpha on the pixels being written (reference src/rwpng.c:557-573) */
-    bool gray = true, opaque = true;
-    for (uint32_t y = 0; y < h && (gray || opaque); y++) {
-        const unsigned char *p = img->row_pointers[y];
-        for (uint32_t x = 0; x < w; x++, p += 4) {
-            if (p[0] != p[1] || p[1] != p[2]) gray = false;
-            if (p[3] < 255) opaque = false;
-        }
-    }
-    const unsigned bpp = gray ? (opaque ? 1 : 2) : (opaque ? 3 : 4);
-    const int ctype = gray ? (opaque ? 0 : 4) : (opaque ? 2 : 6);
+    const int ctype = bpp == 1 ? 0 : bpp == 2 ? 4 : bpp == 3 ? 2 : 6;
     const size_t rb = (size_t)w * bpp;
-
-    unsigned char *cur = malloc(rb ? rb : 1), *prev = malloc(rb ? rb : 1), *filt = malloc(rb + 1);
     unsigned char *zbuf = malloc(IDAT_BYTES);
-    if (!cur || !prev || !filt || !zbuf) {
-        free(cur); free(prev); free(filt); free(zbuf);
-        return OUT_OF_MEMORY_ERROR;
-    }
+    if (!zbuf) return OUT_OF_MEMORY_ERROR;
 
     sink_write(&s, PNG_SIG, 8);
     unsigned char ihdr[13];
@@ -470,44 +460,19 @@ pngloss_error rwpng_write_image24(FILE *outfile, png24_image *img, unsigned char
     write_passthrough(&s, img, RWPNG_AFTER_IHDR);
     write_passthrough(&s, img, RWPNG_AFTER_PLTE);
 
-    /* zlib: level 9, memLevel 9 (reference src/rwpng.c:471-472), the filtered-data strategy, and a window
-     * no larger than the data needs */
     const size_t raw_len = (rb + 1) * (size_t)h;
     int wbits = 15;
     while (wbits > 8 && ((size_t)1 << (wbits - 1)) >= raw_len + 262) wbits--;
     z_stream zs;
     memset(&zs, 0, sizeof zs);
     if (deflateInit2(&zs, Z_BEST_COMPRESSION, Z_DEFLATED, wbits, 9, Z_FILTERED) != Z_OK) {
-        free(cur); free(prev); free(filt); free(zbuf);
+        free(zbuf);
         return LIBPNG_INIT_ERROR;
     }
     zs.next_out = zbuf;
     zs.avail_out = IDAT_BYTES;
-
     for (uint32_t y = 0; y < h; y++) {
-        const unsigned char *p = img->row_pointers[y];
-        for (uint32_t x = 0; x < w; x++, p += 4) {   /* narrow to the colour type (G is luminance) */
-            unsigned char *q = cur + (size_t)x * bpp;
-            switch (bpp) {
-            case 1: q[0] = p[1]; break;
-            case 2: q[0] = p[1]; q[1] = p[3]; break;
-            case 3: q[0] = p[0]; q[1] = p[1]; q[2] = p[2]; break;
-            default: memcpy(q, p, 4); break;
-            }
-        }
-        /* row 0 is always chosen by the heuristic (reference src/rwpng.c:488-495); later rows use the
-         * caller's explicit filter */
-        int type;
-        if (row_filters && y > 0) {
-            const unsigned m = row_filters[y];
-            type = m == 0x10 ? 1 : m == 0x20 ? 2 : m == 0x40 ? 3 : m == 0x80 ? 4 : m == 0x08 ? 0 : -1;
-            if (type < 0) type = rwpng_heuristic_filter(prev, cur, rb, bpp);
-        } else {
-            type = rwpng_heuristic_filter(y ? prev : NULL, cur, rb, bpp);
-        }
-        filt[0] = (unsigned char)type;
-        filter_row(type, filt + 1, cur, y ? prev : NULL, rb, bpp);
-        zs.next_in = filt;
+        zs.next_in = (unsigned char *)next_row(ctx, y);
         zs.avail_in = (uInt)(rb + 1);
         while (zs.avail_in) {
             deflate(&zs, Z_NO_FLUSH);
@@ -517,7 +482,6 @@ pngloss_error rwpng_write_image24(FILE *outfile, png24_image *img, unsigned char
                 zs.avail_out = IDAT_BYTES;
             }
         }
-        unsigned char *t = prev; prev = cur; cur = t;
     }
     for (;;) {
         const int zr = deflate(&zs, Z_FINISH);
@@ -532,8 +496,86 @@ pngloss_error rwpng_write_image24(FILE *outfile, png24_image *img, unsigned char
     deflateEnd(&zs);
     write_passthrough(&s, img, RWPNG_AFTER_IDAT);
     write_chunk(&s, "IEND", NULL, 0);
-    free(cur); free(prev); free(filt); free(zbuf);
+    free(zbuf);
 
     if (s.rc == SUCCESS || s.rc == TOO_LARGE_FILE) img->file_size = s.written;
     return s.rc;
+}
+
+/* rows narrowed and filtered on the CPU */
+struct cpu_rows {
+    png24_image *img;
+    unsigned char *row_filters;
+    unsigned bpp;
+    size_t rb;
+    unsigned char *cur, *prev, *filt;
+};
+
+static const unsigned char *cpu_next_row(void *ctx, uint32_t y) {
+    struct cpu_rows *c = ctx;
+    const unsigned bpp = c->bpp;
+    if (y) { unsigned char *t = c->prev; c->prev = c->cur; c->cur = t; }
+    const unsigned char *p = c->img->row_pointers[y];
+    for (uint32_t x = 0; x < c->img->width; x++, p += 4) {   /* narrow to the colour type (G is luminance) */
+        unsigned char *q = c->cur + (size_t)x * bpp;
+        switch (bpp) {
+        case 1: q[0] = p[1]; break;
+        case 2: q[0] = p[1]; q[1] = p[3]; break;
+        case 3: q[0] = p[0]; q[1] = p[1]; q[2] = p[2]; break;
+        default: memcpy(q, p, 4); break;
+        }
+    }
+    /* row 0 is always chosen by the heuristic (reference src/rwpng.c:488-495); later rows use the
+     * caller's explicit filter */
+    int type;
+    if (c->row_filters && y > 0) {
+        const unsigned m = c->row_filters[y];
+        type = m == 0x10 ? 1 : m == 0x20 ? 2 : m == 0x40 ? 3 : m == 0x80 ? 4 : m == 0x08 ? 0 : -1;
+        if (type < 0) type = rwpng_heuristic_filter(c->prev, c->cur, c->rb, bpp);
+    } else {
+        type = rwpng_heuristic_filter(y ? c->prev : NULL, c->cur, c->rb, bpp);
+    }
+    c->filt[0] = (unsigned char)type;
+    filter_row(type, c->filt + 1, c->cur, y ? c->prev : NULL, c->rb, bpp);
+    return c->filt;
+}
+
+pngloss_error rwpng_write_image24(FILE *outfile, png24_image *img, unsigned char *row_filters) {
+    const uint32_t w = img->width, h = img->height;
+    /* autodetect grayscale and alpha on the pixels being written (reference src/rwpng.c:557-573) */
+    bool gray = true, opaque = true;
+    for (uint32_t y = 0; y < h && (gray || opaque); y++) {
+        const unsigned char *p = img->row_pointers[y];
+        for (uint32_t x = 0; x < w; x++, p += 4) {
+            if (p[0] != p[1] || p[1] != p[2]) gray = false;
+            if (p[3] < 255) opaque = false;
+        }
+    }
+    struct cpu_rows c = {img, row_filters, gray ? (opaque ? 1 : 2) : (opaque ? 3 : 4), 0, NULL, NULL, NULL};
+    c.rb = (size_t)w * c.bpp;
+    c.cur = malloc(c.rb ? c.rb : 1);
+    c.prev = malloc(c.rb ? c.rb : 1);
+    c.filt = malloc(c.rb + 1);
+    pngloss_error rc = OUT_OF_MEMORY_ERROR;
+    if (c.cur && c.prev && c.filt) rc = write_png_stream(outfile, img, c.bpp, cpu_next_row, &c);
+    free(c.cur); free(c.prev); free(c.filt);
+    return rc;
+}
+
+/* rows narrowed and filtered on the GPU (pngloss_b200_image.scanlines) */
+struct gpu_rows {
+    const unsigned char *scan;
+    size_t stride;
+};
+
+static const unsigned char *gpu_next_row(void *ctx, uint32_t y) {
+    const struct gpu_rows *g = ctx;
+    return g->scan + (size_t)y * g->stride;
+}
+
+pngloss_error rwpng_write_scanlines(FILE *outfile, png24_image *img, unsigned bytes_per_pixel,
+                                    const unsigned char *scanlines) {
+    if (bytes_per_pixel < 1 || bytes_per_pixel > 4 || !scanlines) return INVALID_ARGUMENT;
+    struct gpu_rows g = {scanlines, 1 + (size_t)img->width * bytes_per_pixel};
+    return write_png_stream(outfile, img, bytes_per_pixel, gpu_next_row, &g);
 }

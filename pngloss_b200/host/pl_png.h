@@ -77,6 +77,10 @@ typedef struct {
 void rwpng_version_info(FILE *fp);
 pngloss_error rwpng_read_image24(FILE *infile, png24_image *out, bool strip, bool verbose);
 pngloss_error rwpng_write_image24(FILE *outfile, png24_image *image, unsigned char *row_filters);
+/* The same file from rows that are already narrowed and filtered (pngloss_b200_image.scanlines: height rows of
+ * one filter-type byte + width * bytes_per_pixel bytes); image supplies size, colour tags and chunks. */
+pngloss_error rwpng_write_scanlines(FILE *outfile, png24_image *image, unsigned bytes_per_pixel,
+                                    const unsigned char *scanlines);
 void rwpng_free_image24(png24_image *image);
 
 /* The filter (0..4) libpng's default heuristic picks for a row of `rowbytes` bytes with `bpp` bytes per

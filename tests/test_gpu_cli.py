@@ -121,3 +121,30 @@ def test_cli_skip_if_larger(tmp_path, oracle):
     # and a clearly compressible case passes the same option
     assert subprocess.run([CLI, "-s", "40", "--skip-if-larger", src]).returncode == 0
     assert os.path.getsize(str(tmp_path / "in-loss.png")) < os.path.getsize(src)
+
+
+def test_cli_gpu_scanlines_give_the_same_files_as_cpu_filtering(tmp_path, oracle):
+    """The encoder normally receives filtered scanlines from the GPU (K4); with
+    PNGLOSS_CPU_FILTER=1 it narrows and filters the quantised pixels itself, the way the reference's libpng
+    does.  Both must produce byte-identical files, for every colour type."""
+    from checkers import to_bpp
+    imgs = dict(fixture_images(oracle))
+    for bpp in (1, 2, 3, 4):
+        imgs[f"synth{bpp}"] = to_bpp(oracle.synth(300, 41, 90 + bpp), bpp)
+    outs = {}
+    for mode in ("gpu", "cpu"):
+        d = tmp_path / mode
+        d.mkdir()
+        paths = []
+        for key, rgba in imgs.items():
+            p = str(d / f"{key}.png")
+            Image.fromarray(rgba, "RGBA").save(p)
+            paths.append(p)
+        env = dict(os.environ)
+        if mode == "cpu":
+            env["PNGLOSS_CPU_FILTER"] = "1"
+        r = subprocess.run([CLI, "-s", "20", "--", *paths], capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr
+        outs[mode] = {key: open(str(d / f"{key}-loss.png"), "rb").read() for key in imgs}
+    for key in imgs:
+        assert outs["gpu"][key] == outs["cpu"][key], key

@@ -491,3 +491,24 @@ def test_k4_filtered_scanlines(ctx, oracle):
     assert batch.scanline_info(0)["bytes_per_pixel"] == want_bpp == 4
     assert np.array_equal(got, want)
     batch.close()
+
+
+def test_scanlines_through_the_host_buffer_call(ctx, oracle):
+    """pngloss_b200_image.scanlines: the blocking batch call returns filtered scanlines next to (or instead of)
+    the pixels."""
+    from checkers import png_scanlines
+    imgs = [to_bpp(oracle.synth(64, 20, 300 + i), (i % 4) + 1) for i in range(6)]
+    for no_pixels in (False, True):
+        work = [im.copy() for im in imgs]
+        rfs = [np.zeros(20, np.uint8) for _ in imgs]
+        scans = [np.zeros(20 * (1 + 4 * 64), np.uint8) for _ in imgs]
+        res = ctx.optimize_batch(work, rfs, 20, 2, scanlines=scans, no_pixels=no_pixels)
+        for i, im in enumerate(imgs):
+            want_px, want_rf = oracle.optimize(im, 20, 2, True)
+            want_bpp, want_f0, want = png_scanlines(want_px, want_rf)
+            assert res[i]["status"] == 0
+            assert (res[i]["scan_bytes_per_pixel"], res[i]["scan_row0_filter"]) == (want_bpp, want_f0)
+            assert res[i]["scan_bytes"] == want.size
+            assert np.array_equal(scans[i][:want.size].reshape(want.shape), want), i
+            assert np.array_equal(rfs[i], want_rf)
+            assert np.array_equal(work[i], im if no_pixels else want_px), "pixels"
