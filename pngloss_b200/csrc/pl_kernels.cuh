@@ -850,15 +850,7 @@ __device__ __forceinline__ unsigned long long pl_row_pass(PlCtaSmem<LPC, BM> &sm
 // itself, in-place batch) and the original row y is kept in the image's scratch row for the predictions of
 // row y + 1.  The compiler must assume that the stores alias the next loads, so every round of this loop
 // costs a full memory latency: four pixels per thread and round where the row allows it.
-#ifndef PL_COMMIT_MODE
-#define PL_COMMIT_MODE 1
-#endif
-#ifdef PL_COMMIT_NOINLINE
-__device__ __noinline__
-#else
-__device__ __forceinline__
-#endif
-void pl_commit_row(const PlImageDev &im, int w2, int y, int W, int tid) {
+__device__ __forceinline__ void pl_commit_row(const PlImageDev &im, int w2, int y, int W, int tid) {
     const int mode2 = pl_image_mode(im);
     const bool notgray = mode2 >= 3, notopaque = (mode2 & 1) == 0;
     const uchar4 *src = im.cand + (size_t)w2 * W;
@@ -866,7 +858,7 @@ void pl_commit_row(const PlImageDev &im, int w2, int y, int W, int tid) {
     uchar4 *dst = im.out + (size_t)y * W;
     // gray modes: G over R and B (reference src/pngloss_image.c:130-139); opaque modes: alpha 255 (:134,:144)
     const unsigned sel = notgray ? 0x3210u : 0x3111u, amask = notopaque ? 0u : 0xff000000u;
-    if (PL_COMMIT_MODE == 1 && (W & 3) == 0) {   // rows are 16-byte aligned then (256-byte aligned buffers)
+    if ((W & 3) == 0) {   // rows are 16-byte aligned then (256-byte aligned buffers)
         const uint4 *src4 = (const uint4 *)src, *orig4 = (const uint4 *)orig;
         uint4 *dst4 = (uint4 *)dst, *oprev4 = (uint4 *)im.oprev;
         for (int x = tid; x < W / 4; x += PL_K2_THREADS) {
