@@ -512,3 +512,20 @@ def test_scanlines_through_the_host_buffer_call(ctx, oracle):
             assert np.array_equal(scans[i][:want.size].reshape(want.shape), want), i
             assert np.array_equal(rfs[i], want_rf)
             assert np.array_equal(work[i], im if no_pixels else want_px), "pixels"
+
+
+def test_very_wide_rows_fall_back_to_the_scan(ctx, oracle):
+    """Widths of 16384 and more do not fit the bucket table's relative counts: same results, scan kernel
+    (chosen by the host) or in-kernel fall-back (variant forced)."""
+    img = oracle.synth(16400, 3, 55)
+    want_px, want_rf = oracle.optimize(img, 20, 2, True)
+    for lanes, bm in ((1, -1), (1, 1), (8, -1)):
+        ctx.set_lanes(lanes)
+        ctx.set_bucket_maxima(bm)
+        got = img.copy()
+        rf = np.zeros(3, np.uint8)
+        res = ctx.optimize_batch([got], [rf], 20, 2)
+        assert res[0]["status"] == 0
+        assert np.array_equal(got, want_px) and np.array_equal(rf, want_rf), (lanes, bm)
+    ctx.set_lanes(0)
+    ctx.set_bucket_maxima(-1)

@@ -143,6 +143,19 @@ def test_emu_bucket_maxima_paths(emu, oracle):
         assert after[key] > before[key], key
 
 
+def test_emu_bucket_maxima_width_limit(emu, oracle):
+    """Relative counts of a row fit the table's 17-bit field only for widths below 16384: at and beyond that
+    the bucket-maxima kernel must fall back to the scan by itself."""
+    before = emu.counters()
+    img = oracle.synth(16384, 1, 77)
+    compare(emu, oracle, [img], 20, 2, False, BM + 1)
+    after = emu.counters()
+    assert after["bm_lookup"] == before["bm_lookup"] and after["bm_scan"] > before["bm_scan"]
+    narrow = oracle.synth(16380, 1, 78)
+    compare(emu, oracle, [narrow], 20, 2, False, BM + 1)
+    assert emu.counters()["bm_lookup"] > after["bm_lookup"]
+
+
 def test_emu_k1_histograms(emu, oracle):
     """K1's per-channel histograms, folded by colour mode, equal optimize_state_init's table."""
     for bpp in (1, 2, 3, 4):
