@@ -314,33 +314,37 @@ def main():
     e2e = None
     if not a.no_e2e:
         batch.close()                           # give the HBM back; optimize_batch allocates its own
-        # host memory: a pristine copy + the pinned in-place work buffer.  Normally the same images as
-        # above; fewer only if this host could not hold them (then say so in the line).
+        # Host memory: one pinned input buffer that no step modifies and one pinned output buffer, within
+        # 60 % of what the host has free.  When that cannot hold the step's images twice, the output
+        # buffer stays complete and the input buffer holds fewer DISTINCT images: image i is uploaded from
+        # input slot i % m.  Every step still uploads and downloads every image (the byte counts below are
+        # what crosses PCIe); only the content of some uploads repeats.
         img_bytes = w * h * 4
-        n2 = n
+        n2, m = n, n
         try:
             avail = int([ln for ln in open("/proc/meminfo") if ln.startswith("MemAvailable")][0].split()[1]) * 1024
-            n2 = max(1, min(n, int(0.6 * avail / world / (2 * img_bytes))))
+            budget = int(0.6 * avail / world / img_bytes)      # images the two buffers may hold together
+            n2 = max(1, min(n, 2 * budget // 3))               # at least half of the inputs are distinct
+            m = max(1, min(n2, budget - n2))
         except Exception:
             pass
         if world > 1:
-            nmin = torch.tensor([n2], device=f"cuda:{local_rank}")
+            nmin = torch.tensor([n2, m], device=f"cuda:{local_rank}")
             dist.all_reduce(nmin, op=dist.ReduceOp.MIN)
-            n2 = int(nmin.item())
-        # One pinned input buffer that no step modifies and one pinned output buffer: the steps go through
-        # the asynchronous call (pngloss_b200_submit / _wait), two in flight, so that the upload of step
-        # k+1 and the download of step k-1 run under the kernels of step k.  (A step's results are complete
-        # when its wait returns; the next step's download overwrites them afterwards.)
-        src = ctx.pinned_empty((n2, h, w, 4))
+            n2, m = int(nmin[0].item()), int(nmin[1].item())
+        # The steps go through the asynchronous call (pngloss_b200_submit / _wait), two in flight, so that
+        # the upload of step k+1 and the download of step k-1 run under the kernels of step k.  (A step's
+        # results are complete when its wait returns; the next step's download overwrites them afterwards.)
+        src = ctx.pinned_empty((m, h, w, 4))
         dst = [ctx.pinned_empty((n2, h, w, 4))] * 2
-        b2 = pngloss_b200.Batch(ctx, [w] * n2, [h] * n2, in_place=True)
-        for i in range(n2):
+        b2 = pngloss_b200.Batch(ctx, [w] * m, [h] * m, in_place=True)
+        for i in range(m):
             b2.synth(i, seeds[i])
             b2.download_input(i, src[i])
         ctx.sync()
         b2.close()
         filters = [[np.zeros(h, np.uint8) for _ in range(n2)] for _ in range(2)]
-        imgs = [src[i] for i in range(n2)]
+        imgs = [src[i % m] for i in range(n2)]
         outs = [[dst[k][i] for i in range(n2)] for k in range(2)]
 
         def run_steps(count):
@@ -370,6 +374,7 @@ def main():
         e2e = {"value": world * n2 * w * h / (e_step * 1e-3) / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": int(n2 * img_bytes), "d2h_bytes_per_step": int(n2 * (img_bytes + h)),
                "ms_per_step": e_step, "wall_ms_per_step": e_wall / a.steps, "images_per_gpu": n2,
+               "distinct_host_inputs_per_gpu": m,
                "api": "pngloss_b200_submit / pngloss_b200_wait, two steps in flight (pinned host input and "
                       "output buffers; every step uploads its input and downloads its result)"}
         ctx.free_pinned(src)
