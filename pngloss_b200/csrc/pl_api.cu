@@ -481,7 +481,6 @@ static int prepare_run(pngloss_b200_batch *b, unsigned strength, long bleed, cud
     }
     PL_CUDA(ctx, cudaMemcpyAsync(b->dslots, b->hslots.data(), b->hslots.size() * sizeof(int),
                                  cudaMemcpyHostToDevice, stream));
-    PL_CUDA(ctx, cudaMemsetAsync(b->zero_begin, 0, b->zero_bytes, stream));
     return PNGLOSS_B200_SUCCESS;
 }
 
@@ -497,6 +496,11 @@ extern "C" int pngloss_b200_batch_run(pngloss_b200_batch *b, unsigned strength, 
 // The three kernels of a run on the batch's (compute) stream.
 static int launch_run(pngloss_b200_batch *b, unsigned strength, long bleed, int lpc, int nblocks) {
     pngloss_b200_ctx *ctx = b->ctx;
+    // The accumulators are cleared here, on the compute stream, and not with the uploads: a memset is a
+    // kernel, and while another job's K2 is resident (its two CTAs take all of an SM's shared memory) no
+    // other kernel gets onto the SMs - on the upload stream it would hold the next job's pixels back until
+    // that K2 has finished (profiles/r1_e2e_job_timeline.txt).
+    PL_CUDA(ctx, cudaMemsetAsync(b->zero_begin, 0, b->zero_bytes, b->stream));
     // K1: enough row slices per image to fill the machine, capped by the image height
     uint32_t hmin = b->h[0];
     for (size_t i = 1; i < b->n; i++) hmin = std::min(hmin, b->h[i]);
@@ -882,8 +886,8 @@ extern "C" int pngloss_b200_submit(pngloss_b200_ctx *ctx, pngloss_b200_image *im
     job->images = images;
     job->n = n;
 
-    // upload stream: descriptors and cleared accumulators (small copies from pageable memory, which wait for
-    // what the stream already holds - so they go first), then the pixels
+    // upload stream: descriptors (small copies from pageable memory, which wait for what the stream already
+    // holds - so they go first), then the pixels
     int lpc = 0, nblocks = 0;
     for (size_t i = 0; i < n && !rc; i++)
         rc = pngloss_b200_batch_set_mode(b, i, images[i].row_filters == nullptr, images[i].force_bytes_per_pixel);
