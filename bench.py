@@ -335,8 +335,28 @@ def main():
         # The steps go through the asynchronous call (pngloss_b200_submit / _wait), two in flight, so that
         # the upload of step k+1 and the download of step k-1 run under the kernels of step k.  (A step's
         # results are complete when its wait returns; the next step's download overwrites them afterwards.)
-        src = ctx.pinned_empty((m, h, w, 4))
-        dst = [ctx.pinned_empty((n2, h, w, 4))] * 2
+        while True:
+            src = None
+            try:
+                src = ctx.pinned_empty((m, h, w, 4))
+                dst = [ctx.pinned_empty((n2, h, w, 4))] * 2
+                ok = 1
+            except pngloss_b200.PnglossError:
+                if src is not None:
+                    ctx.free_pinned(src)
+                ok = 0
+            if world > 1:                           # all ranks shrink together
+                flag = torch.tensor([ok], device=f"cuda:{local_rank}")
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                if ok and not int(flag.item()):
+                    ctx.free_pinned(src)
+                    ctx.free_pinned(dst[0])
+                ok = int(flag.item())
+            if ok:
+                break
+            if n2 <= 8:
+                raise RuntimeError("bench: no pinned host memory for the end-to-end part")
+            n2, m = n2 // 2, max(1, m // 2)
         b2 = pngloss_b200.Batch(ctx, [w] * m, [h] * m, in_place=True)
         for i in range(m):
             b2.synth(i, seeds[i])
