@@ -529,3 +529,44 @@ def test_very_wide_rows_fall_back_to_the_scan(ctx, oracle):
         assert np.array_equal(got, want_px) and np.array_equal(rf, want_rf), (lanes, bm)
     ctx.set_lanes(0)
     ctx.set_bucket_maxima(-1)
+
+
+def test_host_calls_with_changing_shapes_and_small_memory_budget(oracle):
+    """The host-buffer calls recycle device batches: alternate shapes between calls (the pool must not hand out
+    a batch of the wrong shape), then squeeze the memory budget so that one call runs as several pipelined
+    groups - with scanlines requested, whose device buffer counts against the budget too."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import pngloss_b200
+from checkers import Oracle, png_scanlines
+o = Oracle()
+ctx = pngloss_b200.Context(0)
+want = {}
+for rep in range(3):
+    for (w, h, n) in [(64, 20, 5), (48, 31, 3), (64, 20, 5), (200, 9, 7)]:
+        imgs = [o.synth(w, h, 1000 + 10 * i + w) for i in range(n)]
+        work = [im.copy() for im in imgs]
+        rfs = [np.zeros(h, np.uint8) for _ in imgs]
+        scans = [np.zeros(h * (1 + 4 * w), np.uint8) for _ in imgs]
+        res = ctx.optimize_batch(work, rfs, 20, 2, scanlines=scans)
+        for i, im in enumerate(imgs):
+            key = (w, h, i)
+            if key not in want:
+                px, rf = o.optimize(im, 20, 2, True)
+                want[key] = (px, rf, png_scanlines(px, rf))
+            px, rf, (bpp, f0, sc) = want[key]
+            assert res[i]["status"] == 0 and np.array_equal(work[i], px) and np.array_equal(rfs[i], rf), key
+            assert res[i]["scan_bytes_per_pixel"] == bpp and res[i]["scan_bytes"] == sc.size
+            assert np.array_equal(scans[i][:sc.size].reshape(sc.shape), sc), key
+print("pool ok")
+""" % (ROOT_DIR, os.path.join(ROOT_DIR, "tests"))
+    for budget in (None, "1"):
+        env = dict(os.environ)
+        if budget:
+            env["PNGLOSS_B200_MEM_BUDGET_MB"] = budget
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+        assert r.returncode == 0 and "pool ok" in r.stdout, (budget, r.stderr[-2000:])
