@@ -81,6 +81,10 @@ int pngloss_b200_ctx_set_lanes(pngloss_b200_ctx *ctx, int lanes_per_channel);
  * fall-back, 0 = scan every band, -1 = choose from the strength (default).  A tuning knob, results
  * never depend on it. */
 int pngloss_b200_ctx_set_bucket_maxima(pngloss_b200_ctx *ctx, int mode);
+/* Kernel variant for batches that run one lane per channel with the winner table: 1 / -1 (default) = the lean
+ * kernel (bulk-copy tile ring, three CTAs per SM) where its conditions hold (every width a multiple of 4),
+ * 0 = always the generic kernel.  A tuning knob, results never depend on it. */
+int pngloss_b200_ctx_set_lean(pngloss_b200_ctx *ctx, int mode);
 /* CUDA-event stopwatch on the context's stream (what bench.py times with). */
 int pngloss_b200_ctx_timer_start(pngloss_b200_ctx *ctx);
 int pngloss_b200_ctx_timer_stop(pngloss_b200_ctx *ctx, float *milliseconds);
@@ -165,7 +169,8 @@ void *pngloss_b200_batch_histogram_device(pngloss_b200_batch *b);
  * [2] batch-histogram kernel, [3] whole run.  Valid after finish. */
 int pngloss_b200_batch_timings(pngloss_b200_batch *b, float ms[4]);
 /* Launch geometry of the last run: [0] quantise CTAs, [1] images per CTA, [2] dynamic smem bytes,
- * [3] kernels launched (bits 0-7) and, bit 8, whether the quantise kernel used the bucket-maxima table. */
+ * [3] kernels launched (bits 0-7), bit 8: the quantise kernel used the bucket-maxima table, bit 9: it was the
+ * lean kernel. */
 int pngloss_b200_batch_launch_info(pngloss_b200_batch *b, uint32_t info[4]);
 
 /* Filtered PNG scanlines of the batch's results, ready for deflate (what the reference leaves to libpng

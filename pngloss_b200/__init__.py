@@ -27,7 +27,8 @@ NO_ACCEPTABLE_ROW = 41
 EXPORTS = [
     "optimize_with_rows", "optimize_with_stride", "optimizeForAverageFilter", "optimize_image",
     "pngloss_b200_device_count", "pngloss_b200_ctx_create", "pngloss_b200_ctx_destroy",
-    "pngloss_b200_ctx_error", "pngloss_b200_ctx_set_lanes", "pngloss_b200_ctx_set_bucket_maxima", "pngloss_b200_ctx_timer_start",
+    "pngloss_b200_ctx_error", "pngloss_b200_ctx_set_lanes", "pngloss_b200_ctx_set_bucket_maxima",
+    "pngloss_b200_ctx_set_lean", "pngloss_b200_ctx_timer_start",
     "pngloss_b200_ctx_timer_stop", "pngloss_b200_ctx_sync", "pngloss_b200_host_alloc",
     "pngloss_b200_host_free", "pngloss_b200_optimize_batch", "pngloss_b200_submit", "pngloss_b200_wait",
     "pngloss_b200_batch_create", "pngloss_b200_batch_create_ex",
@@ -97,6 +98,7 @@ def load_library() -> ctypes.CDLL:
     L.pngloss_b200_ctx_error.restype = ctypes.c_char_p
     L.pngloss_b200_ctx_set_lanes.argtypes = [vp, i32]
     L.pngloss_b200_ctx_set_bucket_maxima.argtypes = [vp, i32]
+    L.pngloss_b200_ctx_set_lean.argtypes = [vp, i32]
     L.pngloss_b200_ctx_timer_start.argtypes = [vp]
     L.pngloss_b200_ctx_timer_stop.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     L.pngloss_b200_ctx_sync.argtypes = [vp]
@@ -210,6 +212,10 @@ class Context:
     def set_bucket_maxima(self, mode: int):
         """K2's candidate choice: 1 winner table + scan fall-back, 0 scan only, -1 from the strength."""
         self._check(self.lib.pngloss_b200_ctx_set_bucket_maxima(self.handle, mode))
+
+    def set_lean(self, mode: int):
+        """1 / -1: the lean kernel where it applies (default), 0: always the generic kernel"""
+        self._check(self.lib.pngloss_b200_ctx_set_lean(self.handle, mode))
 
     def timer_start(self):
         self._check(self.lib.pngloss_b200_ctx_timer_start(self.handle))
@@ -388,7 +394,7 @@ class Batch:
         info = (ctypes.c_uint32 * 4)()
         self.ctx._check(self.lib.pngloss_b200_batch_launch_info(self.handle, info))
         return dict(k2_ctas=info[0], images_per_cta=info[1], k2_smem_bytes=info[2], launches=info[3] & 0xff,
-                    bucket_maxima=bool(info[3] & 0x100))
+                    bucket_maxima=bool(info[3] & 0x100), lean=bool(info[3] & 0x200))
 
     def scanlines(self):
         """K4: filtered PNG scanlines of the results, on the device (asynchronous)."""

@@ -24,6 +24,7 @@ struct pngloss_b200_ctx {
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     int lpc = 0;
     int bm = -1;   // bucket-maxima variant of K2: -1 choose from the strength, 0 off, 1 on
+    int lean = -1; // lean kernel (pl_k2_lean) where it applies: -1 yes (default), 0 never, 1 yes
     char err[512] = {0};
     // job API (pngloss_b200_submit / _wait): copy streams, the device batches it recycles, jobs in flight
     cudaStream_t h2d = nullptr, d2h = nullptr;
@@ -152,6 +153,12 @@ extern "C" int pngloss_b200_ctx_set_lanes(pngloss_b200_ctx *ctx, int lpc) {
     if (!ctx || !(lpc == 0 || lpc == 1 || lpc == 2 || lpc == 4 || lpc == 8))
         return PNGLOSS_B200_INVALID_ARGUMENT;
     ctx->lpc = lpc;
+    return PNGLOSS_B200_SUCCESS;
+}
+
+extern "C" int pngloss_b200_ctx_set_lean(pngloss_b200_ctx *ctx, int mode) {
+    if (!ctx || mode < -1 || mode > 1) return PNGLOSS_B200_INVALID_ARGUMENT;
+    ctx->lean = mode;
     return PNGLOSS_B200_SUCCESS;
 }
 
@@ -417,13 +424,10 @@ extern "C" int pngloss_b200_batch_synth(pngloss_b200_batch *b, size_t i, uint64_
 template <int LPC, bool BM>
 static int launch_k2(pngloss_b200_batch *b, int nblocks, unsigned strength, long bleed) {
     pngloss_b200_ctx *ctx = b->ctx;
-    static bool attr_set[16] = {false};
     const size_t smem = sizeof(PlCtaSmem<LPC, BM>) + PL_K2_SMEM_ALIGN;   // slack for the in-kernel alignment
-    if (!attr_set[ctx->device & 15]) {
-        PL_CUDA(ctx, cudaFuncSetAttribute(pl_k2_quantize<LPC, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)smem));
-        attr_set[ctx->device & 15] = true;
-    }
+    // per device and cheap: set on every launch rather than cached in a static shared by the per-GPU threads
+    PL_CUDA(ctx, cudaFuncSetAttribute(pl_k2_quantize<LPC, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
     pl_k2_quantize<LPC, BM><<<nblocks, PL_K2_THREADS, smem, b->stream>>>(b->dimgs, b->dslots, (int)strength,
                                                                           (int)bleed);
     PL_CUDA(ctx, cudaGetLastError());
@@ -432,6 +436,21 @@ static int launch_k2(pngloss_b200_batch *b, int nblocks, unsigned strength, long
     b->info[2] = (uint32_t)smem;
     return PNGLOSS_B200_SUCCESS;
 }
+// the lean kernel: 8 images per CTA, three CTAs per SM (pl_k2_lean.cuh)
+static int launch_k2_lean(pngloss_b200_batch *b, int nblocks, unsigned strength, long bleed) {
+    pngloss_b200_ctx *ctx = b->ctx;
+    const size_t smem = sizeof(PlLeanSmem) + PL_L_SMEM_ALIGN;
+    PL_CUDA(ctx, cudaFuncSetAttribute(pl_k2_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PL_CUDA(ctx, cudaFuncSetAttribute(pl_k2_lean, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+    pl_k2_lean<<<nblocks, PL_K2_THREADS, smem, b->stream>>>(b->dimgs, b->dslots, (int)strength, (int)bleed);
+    PL_CUDA(ctx, cudaGetLastError());
+    b->info[0] = (uint32_t)nblocks;
+    b->info[1] = (uint32_t)PL_L_CPW;
+    b->info[2] = (uint32_t)smem;
+    return PNGLOSS_B200_SUCCESS;
+}
+
 template <int LPC>
 static int launch_k2(pngloss_b200_batch *b, int nblocks, unsigned strength, long bleed, bool bm) {
     return bm ? launch_k2<LPC, true>(b, nblocks, strength, bleed)
@@ -519,7 +538,13 @@ static int launch_run(pngloss_b200_batch *b, unsigned strength, long bleed, int 
     const bool bm = ctx->bm >= 0 ? ctx->bm != 0
                                  : (strength + 1 >= PL_BM_MIN_STEP && strength + 1 <= PL_BM_MAX_STEP &&
                                     wmax < PL_BM_MAX_WIDTH && lpc <= 2);
+    // the lean kernel needs 16-byte aligned rows for its bulk copies
+    bool w4 = true;
+    for (size_t i = 0; i < b->n; i++) w4 = w4 && (b->w[i] & 3u) == 0;
+    const bool lean = lpc == 1 && bm && w4 && wmax < PL_BM_MAX_WIDTH && ctx->lean != 0;
     int rc;
+    if (lean) rc = launch_k2_lean(b, nblocks, strength, bleed);
+    else
     switch (lpc) {
     case 8: rc = launch_k2<8>(b, nblocks, strength, bleed, bm); break;
     case 4: rc = launch_k2<4>(b, nblocks, strength, bleed, bm); break;
@@ -532,7 +557,7 @@ static int launch_run(pngloss_b200_batch *b, unsigned strength, long bleed, int 
                                                                                     b->batch_hist);
     PL_CUDA(ctx, cudaGetLastError());
     PL_CUDA(ctx, cudaEventRecord(b->ev[3], b->stream));
-    b->info[3] = 3 | (bm ? 0x100u : 0u);
+    b->info[3] = 3 | (bm ? 0x100u : 0u) | (lean ? 0x200u : 0u);
     b->ran = true;
     return PNGLOSS_B200_SUCCESS;
 }

@@ -130,3 +130,68 @@ __device__ __forceinline__ int pl_two_ninths(int n) {
     return m < 0 ? -q : q;
 }
 __device__ __forceinline__ int pl_sext16(int v) { return (int)(short)v; }
+// sign extension of the low byte (one PRMT: byte 0, then its sign three times)
+__device__ __forceinline__ int pl_sext8(int v) { return (int)__byte_perm((unsigned)v, 0u, 0x8880u); }
+
+// ---- mbarrier + bulk asynchronous copies (TMA unit, 1-D form: cp.async.bulk, SASS UBLKCP / SYNCS) ------
+// K2's lean variant stages long row segments with these instead of per-lane cp.async: one instruction
+// moves a whole segment global -> shared and reports its bytes to an mbarrier in shared memory.
+// Source, destination and size must be multiples of 16 bytes.
+#ifdef PL_SIMT_EMU
+__device__ __forceinline__ void pl_mbar_init(unsigned long long *bar, unsigned count) { simt::mbar_init(bar, count); }
+__device__ __forceinline__ void pl_mbar_arrive(unsigned long long *bar) { simt::mbar_arrive(bar, 0); }
+__device__ __forceinline__ void pl_mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+    simt::mbar_arrive(bar, bytes);
+}
+__device__ __forceinline__ void pl_mbar_wait(unsigned long long *bar, unsigned parity) {
+    while (!simt::mbar_test(bar, parity)) simt::yield();
+}
+__device__ __forceinline__ void pl_bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes,
+                                            unsigned long long *bar) {
+    simt::bulk_copy(smem_dst, gmem_src, bytes, bar);
+}
+__device__ __forceinline__ void pl_fence_proxy_async() {}
+__device__ __forceinline__ void pl_fence_mbar_init() {}
+#else
+__device__ __forceinline__ void pl_mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count)
+                 : "memory");
+}
+__device__ __forceinline__ void pl_mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void pl_mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+// blocks until the phase of the given parity has completed (the first phase of a barrier has parity 0)
+__device__ __forceinline__ void pl_mbar_wait(unsigned long long *bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "PL_MBAR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra PL_MBAR_DONE_%=;\n"
+        "bra PL_MBAR_WAIT_%=;\n"
+        "PL_MBAR_DONE_%=:\n"
+        "}\n" ::"r"(a),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void pl_bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes,
+                                            unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+// orders this thread's earlier generic-proxy accesses (st.global / st.shared) before later accesses of the
+// async proxy (bulk copies) to the same memory
+__device__ __forceinline__ void pl_fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+__device__ __forceinline__ void pl_fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+#endif

@@ -21,9 +21,10 @@ extern "C" int emu_optimize(unsigned char *rgba, int n, uint32_t w, uint32_t h,
                             int lpc, uint32_t *final_hist, uint32_t *status,
                             unsigned long long *batch_hist, uint32_t *chan_hist_out) {
     // lpc: lanes per channel (8, 4, 2, 1), + 16 for the bucket-maxima variant of K2, + 32 for an
-    // in-place batch (the output buffer is the input buffer)
-    const bool bm = (lpc & 16) != 0, in_place = (lpc & 32) != 0;
+    // in-place batch (the output buffer is the input buffer), + 64 for the lean kernel (pl_k2_lean, lpc 1)
+    const bool bm = (lpc & 16) != 0, in_place = (lpc & 32) != 0, lean = (lpc & 64) != 0;
     lpc &= 15;
+    if (lean && (lpc != 1 || (w & 3))) return -2;
     const size_t npx = (size_t)w * h;
     const size_t ew = (size_t)w + PL_ERR_PAD;
     std::vector<uchar4> out(npx * n);
@@ -61,6 +62,11 @@ extern "C" int emu_optimize(unsigned char *rgba, int n, uint32_t w, uint32_t h,
     const int nblocks = (n + cpw - 1) / cpw;
     std::vector<int> slots((size_t)nblocks * cpw, -1);
     for (int i = 0; i < n; i++) slots[i] = i;
+    if (lean) {
+        const int *dslots = slots.data();
+        simt::launch([&] { pl_k2_lean(dimgs, dslots, strength, bleed); }, dim3(nblocks), dim3(PL_K2_THREADS),
+                     sizeof(PlLeanSmem) + PL_L_SMEM_ALIGN);
+    } else
     switch (lpc) {
     case 8: run_k2<8>(dimgs, slots.data(), nblocks, strength, bleed, bm); break;
     case 4: run_k2<4>(dimgs, slots.data(), nblocks, strength, bleed, bm); break;

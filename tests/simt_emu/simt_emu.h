@@ -58,7 +58,17 @@ struct Slot {
 struct WarpState {
     std::map<unsigned, Slot> slots;
 };
+struct MbarCopy { void *dst; const void *src; unsigned n; };
+struct MbarState {
+    unsigned count = 0;      // arrivals per phase
+    unsigned pending = 0;    // arrivals still missing in the current phase
+    unsigned long long tx = 0;        // bytes announced by expect_tx in the current phase
+    unsigned long long queued = 0;    // bytes of the bulk copies issued against the current phase
+    unsigned phase = 0;
+    std::vector<MbarCopy> copies;
+};
 struct BlockState {
+    std::map<const void *, MbarState> mbars;
     unsigned nthreads = 0;
     unsigned bar_arrived = 0;
     unsigned bar_gen = 0;
@@ -231,7 +241,9 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) {
     unsigned r = 0;
     for (int i = 0; i < 4; i++) {
         unsigned sel = (s >> (4 * i)) & 7u;
-        r |= (unsigned)((src >> (8 * sel)) & 0xffu) << (8 * i);
+        unsigned byte = (unsigned)((src >> (8 * sel)) & 0xffu);
+        if ((s >> (4 * i)) & 8u) byte = (byte & 0x80u) ? 0xffu : 0u;   // sign-replicate mode
+        r |= byte << (8 * i);
     }
     return r;
 }
@@ -251,5 +263,63 @@ static inline void cp_async(void *dst, const void *src, unsigned n) { cur->pendi
 static inline void cp_async_wait_all() {
     for (auto &c : cur->pending) memcpy(c.dst, c.src, c.n);
     cur->pending.clear();
+}
+}  // namespace simt
+
+// ---- mbarrier + bulk copy model ---------------------------------------------------------------------------
+// Default: the bytes of a bulk copy land at the last possible moment - when a waiter finds the phase
+// complete (worst case for a consumer that reads before it waited).  With PL_EMU_BULK_EARLY=1 in the
+// environment they land the moment the copy is issued (worst case for a producer that refills a buffer
+// somebody still reads).
+namespace simt {
+static inline bool bulk_early() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("PL_EMU_BULK_EARLY"); v = e && *e == '1'; }
+    return v != 0;
+}
+static inline MbarState &mbar_of(const void *bar) {
+    auto it = blk.mbars.find(bar);
+    if (it == blk.mbars.end()) { fprintf(stderr, "simt_emu: mbarrier %p used before init\n", bar); abort(); }
+    return it->second;
+}
+static inline void mbar_init(const void *bar, unsigned count) {
+    MbarState st;
+    st.count = st.pending = count;
+    blk.mbars[bar] = st;
+    progress++;
+}
+static inline void mbar_arrive(const void *bar, unsigned tx_bytes) {
+    MbarState &m = mbar_of(bar);
+    if (!m.pending) { fprintf(stderr, "simt_emu: too many arrivals on mbarrier %p\n", bar); abort(); }
+    m.pending--;
+    m.tx += tx_bytes;
+    progress++;
+}
+static inline void bulk_copy(void *dst, const void *src, unsigned n, const void *bar) {
+    if (n == 0 || (n & 15u) || ((uintptr_t)dst & 15u) || ((uintptr_t)src & 15u)) {
+        fprintf(stderr, "simt_emu: bulk copy needs 16-byte aligned dst/src/size (%p, %p, %u)\n", dst, src, n);
+        abort();
+    }
+    MbarState &m = mbar_of(bar);
+    m.queued += n;
+    if (bulk_early()) memcpy(dst, src, n);
+    else m.copies.push_back({dst, src, n});
+    progress++;
+}
+// true once the phase of parity `parity` has completed
+static inline bool mbar_test(const void *bar, unsigned parity) {
+    MbarState &m = mbar_of(bar);
+    if (m.pending == 0 && m.queued == m.tx) {
+        for (auto &c : m.copies) memcpy(c.dst, c.src, c.n);
+        m.copies.clear();
+        m.pending = m.count;
+        m.tx = m.queued = 0;
+        m.phase ^= 1u;
+        progress++;
+    } else if (m.pending == 0 && m.queued > m.tx) {
+        fprintf(stderr, "simt_emu: mbarrier %p got more bytes than expect_tx announced\n", bar);
+        abort();
+    }
+    return (m.phase & 1u) != (parity & 1u);
 }
 }  // namespace simt

@@ -190,3 +190,111 @@ def test_emu_k4_scanlines(emu, oracle):
             assert np.array_equal(got, want), (w, h, bpp)
             dec = np.asarray(Image.open(io.BytesIO(png_from_scanlines(w, h, got_bpp, got))).convert("RGBA"))
             assert np.array_equal(dec, px), (w, h, bpp)
+
+
+# ---- the lean kernel (pl_k2_lean.cuh): bulk-copy ring, 16-bit count increments, direct bucket update ----------
+LEAN = 64 + BM + 1   # emu flag: pl_k2_lean (one lane per channel, bucket maxima)
+
+LEAN_CASES = [  # w, h, seed, bpp, strength, bleed, null_filters  (widths are multiples of 4)
+    (16, 6, 3, 4, 20, 2, False),     # one full tile
+    (36, 9, 5, 4, 20, 2, False),     # three tiles, ragged tail of 4
+    (64, 7, 7, 3, 20, 2, False),
+    (32, 8, 9, 2, 20, 2, False),
+    (40, 8, 11, 1, 20, 2, False),
+    (100, 5, 13, 4, 85, 1, True),
+    (20, 5, 15, 4, 255, 2, False),   # no bucket table at this strength: every byte scans
+    (12, 9, 17, 4, 0, 2, False),
+    (4, 1, 3, 4, 20, 2, False),
+    (4, 16, 3, 4, 20, 2, False),
+    (48, 1, 3, 4, 20, 2, False),
+    (28, 4, 19, 4, 15, 32767, False),
+    (68, 3, 21, 2, 40, 3, True),
+    (132, 4, 23, 4, 126, 2, False),  # the largest strength with a table
+]
+
+
+@pytest.mark.parametrize("case", LEAN_CASES, ids=lambda c: "w%d-h%d-seed%d-bpp%d-s%d-b%d-null%d" % c)
+def test_emu_lean_single_image(emu, oracle, case):
+    w, h, seed, bpp, s, b, nf = case
+    img = to_bpp(oracle.synth(w, h, seed), bpp)
+    compare(emu, oracle, [img], s, b, nf, LEAN)
+
+
+@pytest.mark.parametrize("flags", [LEAN, IN_PLACE + LEAN])
+def test_emu_lean_batch_mixed_modes(emu, oracle, flags):
+    """11 images = one full CTA of 8 and a partially filled one, every bytes-per-pixel mode."""
+    imgs = [to_bpp(oracle.synth(52, 6, 100 + i), (i % 4) + 1) for i in range(11)]
+    compare(emu, oracle, imgs, 20, 2, False, flags)
+
+
+def test_emu_lean_retry_path(emu, oracle):
+    rng = np.random.default_rng(7)
+    imgs, retried = [], 0
+    while len(imgs) < 16:
+        img = rng.integers(0, 256, (3, 8, 4), dtype=np.uint8)
+        img = to_bpp(img, int(rng.integers(1, 5)))
+        _, _, tr = oracle.optimize(img, 20, 2, False, trace=True)
+        hit = bool((tr["row_strength"] != 20).any())
+        if hit or len(imgs) % 2 == 1:
+            imgs.append(img)
+            retried += hit
+    assert retried >= 4
+    got = compare(emu, oracle, imgs, 20, 2, True, LEAN)
+    assert (got["status"][:, 2] > 0).sum() == retried
+
+
+def test_emu_lean_noise_ties_and_paths(emu, oracle):
+    """Frequency ties, noise (bands that wrap past +-128: the seam), fully transparent pixels, clamped bands;
+    the look-up, the scan, the direct and the general bucket update must all have run."""
+    before = emu.counters()
+    rng = np.random.default_rng(11)
+    few = (rng.integers(0, 4, (6, 24, 4)) * 85).astype(np.uint8)
+    noise = rng.integers(0, 256, (6, 24, 4), dtype=np.uint8)
+    holes = noise.copy()
+    holes[rng.random((6, 24)) < 0.3, 3] = 0
+    dark = (rng.integers(0, 30, (6, 24, 4))).astype(np.uint8)
+    bright = (255 - rng.integers(0, 30, (6, 24, 4))).astype(np.uint8)
+    smooth = oracle.synth(24, 6, 5)
+    imgs = [few, noise, holes, to_bpp(holes, 2), dark, bright, smooth, to_bpp(noise, 1), to_bpp(dark, 3)]
+    for s, b, nf in ((19, 2, False), (15, 1, False), (63, 3, True), (126, 2, False), (200, 1, True)):
+        compare(emu, oracle, imgs, s, b, nf, LEAN)
+    after = emu.counters()
+    for key in ("bm_lookup", "bm_scan", "bm_fast_update", "bm_general_update", "fixup_replay", "fixup_skipped",
+                "taps_table", "taps_computed"):
+        assert after[key] > before[key], key
+
+
+def test_emu_lean_early_bulk_copies(oracle):
+    """The same kernel with bulk copies that land the moment they are issued (the default lands them at the
+    wait): a tile that is refilled while a warp still reads it would show up here."""
+    import subprocess, sys, os, textwrap
+    code = textwrap.dedent("""
+        import sys, numpy as np
+        sys.path.insert(0, %r)
+        from checkers import Oracle, to_bpp
+        from emu import Emu
+        emu, oracle = Emu(), Oracle()
+        imgs = [to_bpp(oracle.synth(84, 5, 200 + i), (i %% 4) + 1) for i in range(9)]
+        got = emu.optimize(imgs, 20, 2, False, %d)
+        for i, img in enumerate(imgs):
+            px, rf = oracle.optimize(img, 20, 2, True)
+            assert np.array_equal(got["pixels"][i], px) and np.array_equal(got["filters"][i], rf), i
+        print("ok")
+    """) % (os.path.dirname(os.path.abspath(__file__)), LEAN)
+    env = dict(os.environ, PL_EMU_BULK_EARLY="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_emu_lean_full_rgba_ctas(emu, oracle):
+    """Eight live RGBA images per CTA: the all-lanes-active specialisation of the lean row pass (two full CTAs),
+    with transparent holes, noise and the retry path (null filters) in the mix."""
+    rng = np.random.default_rng(23)
+    imgs = [oracle.synth(44, 5, 300 + i) for i in range(12)]
+    for k in range(4):
+        n = rng.integers(0, 256, (5, 44, 4), dtype=np.uint8)
+        n[..., 3] = np.where(rng.random((5, 44)) < 0.2, 0, np.maximum(n[..., 3], 1))
+        n[0, 0, 3] = 7   # stays on the RGBA path
+        imgs.append(n)
+    compare(emu, oracle, imgs, 20, 2, False, LEAN)
+    compare(emu, oracle, imgs, 31, 1, True, LEAN)

@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--images", default="148,296,592")
     ap.add_argument("--lanes", default="8,4,2,1")
     ap.add_argument("--bm", default="-1", help="bucket-maxima modes to sweep: -1 library default, 0 off, 1 on")
+    ap.add_argument("--lean", default="-1", help="lean-kernel modes to sweep: -1 library default, 0 generic kernel, 1 lean")
     ap.add_argument("--strength", type=int, default=20)
     ap.add_argument("--reps", type=int, default=1)
     ap.add_argument("--profile", action="store_true", help="with a -DPL_K2_PROFILE build: per-filter busy cycles")
@@ -27,9 +28,11 @@ def main():
         for i in range(n):
             batch.synth(i, 4 + i)
         ctx.sync()
-        for lanes, bm in [(int(x), int(m)) for x in a.lanes.split(",") for m in a.bm.split(",")]:
+        for lanes, bm, lean in [(int(x), int(m), int(l)) for x in a.lanes.split(",") for m in a.bm.split(",")
+                                for l in a.lean.split(",")]:
             ctx.set_lanes(lanes)
             ctx.set_bucket_maxima(bm)
+            ctx.set_lean(lean)
             best = None
             for _ in range(a.reps + 1):       # first run is the warm-up
                 batch.run(a.strength, 2)
@@ -45,7 +48,7 @@ def main():
                                   "total_kcycles": int(h0[10]),
                                   "busy_frac": [round(b / max(1, int(h0[10])), 3) for b in busy]}), flush=True)
             px = n * a.width * a.height
-            print(json.dumps({"images": n, "w": a.width, "h": a.height, "lanes": lanes, "bm": bm,
+            print(json.dumps({"images": n, "w": a.width, "h": a.height, "lanes": lanes, "bm": bm, "lean": lean,
                               "k1_ms": round(best["k1_hist_ms"], 3), "k2_ms": round(best["k2_quantize_ms"], 3),
                               "k2_mpx_s": round(px / best["k2_quantize_ms"] / 1e3, 1),
                               "k1_gpx_s": round(px / best["k1_hist_ms"] / 1e6, 2),
