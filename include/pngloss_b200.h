@@ -187,6 +187,34 @@ int pngloss_b200_batch_scanline_info(pngloss_b200_batch *b, size_t i, uint32_t *
 int pngloss_b200_batch_download_scanlines(pngloss_b200_batch *b, size_t i, unsigned char *dst,
                                           size_t capacity);   /* async copy of `bytes` bytes */
 
+/* ------------------------------------------------------------------------------------------------
+ * Part 3 - multi-GPU (new).  Images are the shard unit and need no exchange; the one collective of the path
+ * is the sum of the batch symbol histograms over all GPUs (256 x u64) - the batch-level form of the
+ * reference's "used N unique symbols" report (src/pngloss_image.c:315-325).  The library issues it itself as
+ * an NCCL all-reduce on the context's stream; NCCL is loaded at run time (libnccl.so.2, or the path in
+ * PNGLOSS_B200_NCCL_LIB), so single-GPU use does not need it.
+ * ---------------------------------------------------------------------------------------------- */
+#define PNGLOSS_B200_COMM_ID_BYTES 128
+/* One process per GPU: rank 0 creates an id, hands it to the other ranks by whatever means the launcher has,
+ * and every rank joins with its context. */
+int pngloss_b200_comm_unique_id(unsigned char id[PNGLOSS_B200_COMM_ID_BYTES]);
+int pngloss_b200_comm_init_rank(pngloss_b200_ctx *ctx, int nranks, int rank,
+                                const unsigned char id[PNGLOSS_B200_COMM_ID_BYTES]);
+/* One process, one context (and host thread) per GPU. */
+int pngloss_b200_comm_init_all(pngloss_b200_ctx **ctxs, int n);
+void pngloss_b200_comm_destroy(pngloss_b200_ctx *ctx);
+int pngloss_b200_comm_size(const pngloss_b200_ctx *ctx);   /* 0 = no communicator */
+/* Sum of the batch histogram over all ranks, in place on the device, asynchronous on the context's stream
+ * (call after pngloss_b200_batch_run; read with pngloss_b200_batch_histogram after _finish).  Every rank must
+ * call it once per run. */
+int pngloss_b200_batch_allreduce_histogram(pngloss_b200_batch *b);
+/* Up to 256 host values reduced over the ranks, blocking (a barrier when the result is ignored).
+ * op: 0 sum, 1 max, 2 min. */
+int pngloss_b200_comm_allreduce_u64(pngloss_b200_ctx *ctx, uint64_t *values, size_t n, int op);
+
+/* Benchmark helper: overwrite a buffer larger than the L2 cache on the context's stream. */
+int pngloss_b200_ctx_flush_l2(pngloss_b200_ctx *ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,7 +40,30 @@ EXPORTS = [
     "pngloss_b200_batch_histogram_device", "pngloss_b200_batch_timings",
     "pngloss_b200_batch_launch_info", "pngloss_b200_batch_scanlines", "pngloss_b200_batch_scanline_info",
     "pngloss_b200_batch_download_scanlines",
+    "pngloss_b200_comm_unique_id", "pngloss_b200_comm_init_rank", "pngloss_b200_comm_init_all",
+    "pngloss_b200_comm_destroy", "pngloss_b200_comm_size", "pngloss_b200_batch_allreduce_histogram",
+    "pngloss_b200_comm_allreduce_u64", "pngloss_b200_ctx_flush_l2",
 ]
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """NCCL unique id for pngloss_b200_comm_init_rank (rank 0 creates it and hands it to the other ranks)."""
+    buf = ctypes.create_string_buffer(COMM_ID_BYTES)
+    rc = load_library().pngloss_b200_comm_unique_id(buf)
+    if rc:
+        raise PnglossError(rc, "pngloss_b200_comm_unique_id (is libnccl.so.2 loadable?)")
+    return buf.raw
+
+
+def comm_init_all(contexts: "Sequence[Context]"):
+    """One process driving several GPUs: one communicator over the given contexts (one per device)."""
+    arr = (ctypes.c_void_p * len(contexts))(*[c.handle for c in contexts])
+    rc = load_library().pngloss_b200_comm_init_all(arr, len(contexts))
+    if rc:
+        raise PnglossError(rc, contexts[0].lib.pngloss_b200_ctx_error(contexts[0].handle).decode())
 
 
 class PnglossError(RuntimeError):
@@ -134,6 +157,15 @@ def load_library() -> ctypes.CDLL:
     L.pngloss_b200_batch_scanline_info.argtypes = [vp, sz, ctypes.POINTER(u32), ctypes.POINTER(u32),
                                                    ctypes.POINTER(sz), ctypes.POINTER(ctypes.c_float)]
     L.pngloss_b200_batch_download_scanlines.argtypes = [vp, sz, vp, sz]
+    L.pngloss_b200_comm_unique_id.argtypes = [vp]
+    L.pngloss_b200_comm_init_rank.argtypes = [vp, i32, i32, vp]
+    L.pngloss_b200_comm_init_all.argtypes = [ctypes.POINTER(vp), i32]
+    L.pngloss_b200_comm_destroy.argtypes = [vp]
+    L.pngloss_b200_comm_destroy.restype = None
+    L.pngloss_b200_comm_size.argtypes = [vp]
+    L.pngloss_b200_batch_allreduce_histogram.argtypes = [vp]
+    L.pngloss_b200_comm_allreduce_u64.argtypes = [vp, vp, sz, i32]
+    L.pngloss_b200_ctx_flush_l2.argtypes = [vp]
     _lib = L
     return L
 
@@ -216,6 +248,29 @@ class Context:
     def set_lean(self, mode: int):
         """1 / -1: the lean kernel where it applies (default), 0: always the generic kernel"""
         self._check(self.lib.pngloss_b200_ctx_set_lean(self.handle, mode))
+
+    # ---- multi-GPU: the library's own NCCL communicator (pl_comm.cuh) --------------------------------------
+    def comm_init_rank(self, nranks: int, rank: int, unique_id: bytes):
+        assert len(unique_id) == COMM_ID_BYTES
+        buf = ctypes.create_string_buffer(unique_id, COMM_ID_BYTES)
+        self._check(self.lib.pngloss_b200_comm_init_rank(self.handle, nranks, rank, buf))
+
+    def comm_size(self) -> int:
+        return self.lib.pngloss_b200_comm_size(self.handle)
+
+    def comm_allreduce(self, values, op: str = "sum") -> np.ndarray:
+        """Up to 256 host integers reduced over the ranks (blocking); op in sum / max / min."""
+        a = np.ascontiguousarray(np.asarray(values, np.uint64).reshape(-1)).copy()
+        self._check(self.lib.pngloss_b200_comm_allreduce_u64(self.handle, a.ctypes.data, a.size,
+                                                            {"sum": 0, "max": 1, "min": 2}[op]))
+        return a
+
+    def barrier(self):
+        if self.comm_size() > 1:
+            self.comm_allreduce([0])
+
+    def flush_l2(self):
+        self._check(self.lib.pngloss_b200_ctx_flush_l2(self.handle))
 
     def timer_start(self):
         self._check(self.lib.pngloss_b200_ctx_timer_start(self.handle))
@@ -381,6 +436,10 @@ class Batch:
         out = np.zeros(256, np.uint64)
         self.ctx._check(self.lib.pngloss_b200_batch_histogram(self.handle, out.ctypes.data))
         return out
+
+    def allreduce_histogram(self):
+        """NCCL sum of the batch histogram over all ranks, in place on the device (asynchronous)."""
+        self.ctx._check(self.lib.pngloss_b200_batch_allreduce_histogram(self.handle))
 
     def histogram_device_ptr(self) -> int:
         return self.lib.pngloss_b200_batch_histogram_device(self.handle)

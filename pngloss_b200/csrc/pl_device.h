@@ -130,8 +130,8 @@ __device__ __forceinline__ int pl_two_ninths(int n) {
     return m < 0 ? -q : q;
 }
 __device__ __forceinline__ int pl_sext16(int v) { return (int)(short)v; }
-// sign extension of the low byte (one PRMT: byte 0, then its sign three times)
-__device__ __forceinline__ int pl_sext8(int v) { return (int)__byte_perm((unsigned)v, 0u, 0x8880u); }
+// sign extension of the low byte
+__device__ __forceinline__ int pl_sext8(int v) { return (int)(((unsigned)v & 255u) ^ 128u) - 128; }
 
 // ---- mbarrier + bulk asynchronous copies (TMA unit, 1-D form: cp.async.bulk, SASS UBLKCP / SYNCS) ------
 // K2's lean variant stages long row segments with these instead of per-lane cp.async: one instruction

@@ -23,6 +23,7 @@
 //
 // Replaces the same reference code as K2: src/pngloss_image.c:159-309, src/optimize_state.c:114-361,390-562.
 #pragma once
+#include <stddef.h>
 
 #define PL_L_T 16        // pixels per tile
 #define PL_L_STAGES 2    // tiles in the input ring
@@ -176,20 +177,30 @@ __device__ __forceinline__ unsigned long long pl_lean_row_pass(PlLeanSmem &sm, c
         const int npx = min(PL_L_T, W - x0);
         pl_mbar_wait(&sm.full[s], ph);
 
-        int o_n = ((const unsigned char *)&st.orig[ci][PL_L_HALO])[ch];
-        int a_n = ((const unsigned char *)&st.na[ci][PL_L_HALO])[ch];
-        int e0_n = pl_chan16(st.e0[ci][0], ch);
-        int e1_n = pl_chan16(st.e1[ci][0], ch);
+        // this lane's channel of the tile's pixels / error cells, as flat pointers: the look-ahead below reads one
+        // element past the tile (into the next row of the staging arrays, never used)
+        const unsigned char *po = (const unsigned char *)&st + offsetof(PlLeanStage, orig) +
+                                  (ci * (PL_L_T + PL_L_HALO) + PL_L_HALO) * 4 + ch;
+        const unsigned char *pa = (const unsigned char *)&st + offsetof(PlLeanStage, na) +
+                                  (ci * (PL_L_T + PL_L_HALO) + PL_L_HALO) * 4 + ch;
+        const short *pe0 = (const short *)((const unsigned char *)&st + offsetof(PlLeanStage, e0)) +
+                           ci * (PL_L_T + 2) * 4 + ch;
+        const short *pe1 = (const short *)((const unsigned char *)&st + offsetof(PlLeanStage, e1)) +
+                           ci * (PL_L_T + 2) * 4 + ch;
+        int o_n = po[0];
+        int a_n = pa[0];
+        int e0_n = pe0[0];
+        int e1_n = pe1[0];
         for (int i = 0; i < npx; i++) {
             const int o = o_n, a = a_n;
             a2 = e0_n;
             b4 = e1_n;
             c3 = 0;
             // prefetch pixel i+1, off the dependency chain (one slot beyond the tile is readable padding)
-            o_n = ((const unsigned char *)&st.orig[ci][PL_L_HALO + i + 1])[ch];
-            a_n = ((const unsigned char *)&st.na[ci][PL_L_HALO + i + 1])[ch];
-            e0_n = pl_chan16(st.e0[ci][i + 1], ch);
-            e1_n = pl_chan16(st.e1[ci][i + 1], ch);
+            o_n = po[(i + 1) * 4];
+            a_n = pa[(i + 1) * 4];
+            e0_n = pe0[(i + 1) * 4];
+            e1_n = pe1[(i + 1) * 4];
 
             // ---- band of admissible symbols (reference src/optimize_state.c:158-210) ---------------
             // wrap (:175-182): the exact symbol orig - predicted, brought into [-128, 127], is the signed
@@ -613,7 +624,8 @@ pl_k2_lean(const PlImageDev *imgs, const int *slots, int strength, int bleed) {
                        : pl_lean_row_pass<false>(sm, cn, F, W, y, y & 1, adaptive, bleed_magic, use);
             use += (unsigned)ntiles;
             if (ch == 0 && cn.live) sm.cost[ci][F] = cost;
-            pl_fence_proxy_async();   // this thread's candidate / error rows, before the next pass's bulk reads
+            __threadfence();          // this thread's candidate / error rows reach L2 (the TMA unit reads there) ...
+            pl_fence_proxy_async();   // ... and are ordered before the next pass's bulk reads
             __syncthreads();
 
             // ---- pick the winner of every image that ran this pass (reference :257-263) ------------------
@@ -670,6 +682,7 @@ pl_k2_lean(const PlImageDev *imgs, const int *slots, int strength, int bleed) {
                 }
             }
             cn.live = pending;
+            __threadfence();
             pl_fence_proxy_async();   // the committed row, before the next row's bulk reads
             __syncthreads();
             if (tid == 0) sm.retry = 0;

@@ -570,3 +570,94 @@ print("pool ok")
             env["PNGLOSS_B200_MEM_BUDGET_MB"] = budget
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
         assert r.returncode == 0 and "pool ok" in r.stdout, (budget, r.stderr[-2000:])
+
+
+# ---- the large-batch kernel (pl_k2_lean.cuh) ---------------------------------------------------------------
+@pytest.mark.parametrize("lean", [1, 0], ids=["lean", "generic"])
+def test_lean_kernel_golden_and_random(ctx, oracle, lean):
+    """The large-batch kernel (pl_k2_lean: bulk-copy tile ring, 16-bit count increments, three CTAs per SM)
+    against the reference's goldens and the oracle: the goldens whose width is a multiple of 4 in one batch per
+    (strength, bleed) (mixed sizes, colour modes, NULL filters), 19 random images of every mode in full and
+    ragged CTAs, and the same through the generic kernel."""
+    ctx.set_lanes(1)
+    ctx.set_bucket_maxima(1)
+    ctx.set_lean(lean)
+    groups = {}
+    for c in cases("small", "medium"):
+        groups.setdefault((c["strength"], c["bleed"]), []).append(c)
+    for (s, b), cs in groups.items():
+        cs = [c for c in cs if load_input(c, oracle).shape[1] % 4 == 0]
+        if not cs:
+            continue
+        imgs = [load_input(c, oracle).copy() for c in cs]
+        rfs = [np.zeros(im.shape[0], np.uint8) if c["filters"] else None for c, im in zip(cs, imgs)]
+        res = ctx.optimize_batch(imgs, rfs, s, b)
+        for c, im, rf, r in zip(cs, imgs, rfs, res):
+            assert r["status"] == 0
+            assert sha16(im) == c["px_sha"], case_id(c)
+            if c["filters"]:
+                assert sha16(rf) == c["filt_sha"], case_id(c)
+    rng = np.random.default_rng(99)
+    ran_lean = 0
+    for (w, h, s, b) in [(64, 40, 20, 2), (100, 17, 19, 1), (36, 33, 63, 3), (260, 9, 126, 2), (48, 12, 15, 2)]:
+        n = 19
+        imgs = []
+        for i in range(n):
+            kind = i % 3
+            if kind == 0:
+                a = oracle.synth(w, h, 500 + i)
+            elif kind == 1:
+                a = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+                a[rng.random((h, w)) < 0.2, 3] = 0
+            else:
+                a = (rng.integers(0, 6, (h, w, 4)) * 51).astype(np.uint8)
+            imgs.append(to_bpp(a, 4 if i < 9 else (i % 4) + 1))
+        batch = pngloss_b200.Batch(ctx, [w] * n, [h] * n)
+        for i, a in enumerate(imgs):
+            batch.upload(i, a)
+        batch.run(s, b)
+        st, _, _ = batch.finish()
+        assert (st == 0).all()
+        info = batch.launch_info()
+        assert info["lean"] == bool(lean) and info["images_per_cta"] == 8
+        ran_lean += info["lean"]
+        out = np.zeros((h, w, 4), np.uint8)
+        rf = np.zeros(h, np.uint8)
+        for i, a in enumerate(imgs):
+            batch.download(i, out, rf)
+            ctx.sync()
+            px, want_rf = oracle.optimize(a, s, b, True)
+            assert np.array_equal(out, px) and np.array_equal(rf, want_rf), (w, h, s, b, i)
+        batch.close()
+    assert ran_lean == (5 if lean else 0)
+    ctx.set_lanes(0)
+    ctx.set_bucket_maxima(-1)
+    ctx.set_lean(-1)
+
+
+def test_lean_kernel_4k_golden_24_images(ctx, oracle):
+    """Three full CTAs of the lean kernel on the full-size 4K golden vector, as an in-place batch: replicas must
+    hash to the reference's output (pixels and row filters)."""
+    c = [c for c in cases("large") if c["src"]["w"] == 3840 and c["strength"] == 20][0]
+    src = c["src"]
+    n = 24
+    ctx.set_lanes(1)
+    ctx.set_bucket_maxima(1)
+    ctx.set_lean(1)
+    batch = pngloss_b200.Batch(ctx, [src["w"]] * n, [src["h"]] * n, in_place=True)
+    for i in range(n):
+        batch.synth(i, src["seed"])
+    batch.run(c["strength"], c["bleed"])
+    st, bpp, _ = batch.finish()
+    assert (st == 0).all() and (bpp == 4).all()
+    assert batch.launch_info()["lean"]
+    out = np.zeros((src["h"], src["w"], 4), np.uint8)
+    rf = np.zeros(src["h"], np.uint8)
+    for i in range(0, n, 5):
+        batch.download(i, out, rf)
+        ctx.sync()
+        assert sha16(out) == c["px_sha"] and sha16(rf) == c["filt_sha"], i
+    batch.close()
+    ctx.set_lanes(0)
+    ctx.set_bucket_maxima(-1)
+    ctx.set_lean(-1)
