@@ -173,7 +173,7 @@ __device__ __forceinline__ void pl_mbar_wait(unsigned long long *bar, unsigned p
         "{\n"
         ".reg .pred p;\n"
         "PL_MBAR_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n"   /* suspend-time hint (ns): sleep, do not spin */
         "@p bra PL_MBAR_DONE_%=;\n"
         "bra PL_MBAR_WAIT_%=;\n"
         "PL_MBAR_DONE_%=:\n"

@@ -52,7 +52,7 @@ struct PlLeanSmem {
     PlLeanStage stage[PL_L_STAGES];                     // first member: bulk-copy destinations, 16-byte aligned
     unsigned long long full[PL_L_STAGES];               // mbarrier: the tile's bytes have landed
     unsigned long long empty[PL_L_STAGES];              // mbarrier: all five warps are done with the tile
-    unsigned released[PL_L_STAGES];                     // elects the warp that releases a tile last
+    unsigned released[PL_L_STAGES];                     // release counter: elects the warp that refills a tile
     int prevw[PL_L_CPW];                                // winner of the previous row (whose error rows to read)
     int win[PL_L_CPW];
     unsigned livemask;                                  // images that take part in the current pass
@@ -323,8 +323,10 @@ __device__ __forceinline__ unsigned long long pl_lean_row_pass(PlLeanSmem &sm, c
                     const unsigned now = bc + 1u;
                     const unsigned rank7 = (bl >> (PL_KEY_RANK_SHIFT - 7)) & (255u << 7);
                     const int s8 = pl_sext8(sym);
-                    if (tvalid && s8 > bmc.seam_n && s8 < bmc.seam_p) {
-                        // not in the seam: sym == s8 lies in the band that was looked up, i.e. in bucket tl
+                    if (tvalid && (unsigned)(sym - lo_u) <= (unsigned)q && s8 > bmc.seam_n && s8 < bmc.seam_p) {
+                        // the usual case: the symbol lies in the band that was looked up, i.e. in bucket tl (a band
+                        // that the clamp emptied collapses onto a value outside of it), and not in the seam, so
+                        // that sym == s8 and tl is its only bucket
                         PL_EMU_COUNT(PL_CNT_BM_FASTUPD);
                         if (now >= base_l)
                             atomicMax(&bmrow[tl].x, ((now - base_l) << PL_BM_COUNT_SHIFT) | rank7 |
@@ -449,17 +451,18 @@ __device__ __forceinline__ unsigned long long pl_lean_row_pass(PlLeanSmem &sm, c
         __syncwarp();
         if (ch == 0 && live) wo.back[ci][PL_L_HALO - 1] = wo.back[ci][PL_L_HALO + npx - 1];
 
-        // ---- release the tile; the warp that does so last refills the stage -----------------------------
-        unsigned last = 0;
+        // ---- release the tile.  The warp that does so FIRST (the fastest of the five) waits for the other four and
+        // refills the stage: the slowest warp - the one everybody waits for at the end of the row - never issues
+        // copies and never waits for a tile (the refill it needs next was issued a whole tile ago).
+        unsigned order = 1;
         if (lane == 0) {
+            order = atomicAdd(&sm.released[s], 1u) % PL_K2_WARPS;   // counts up forever: 5 releases per use of a stage
             pl_mbar_arrive(&sm.empty[s]);
-            last = (unsigned)(atomicAdd(&sm.released[s], 1u) == PL_K2_WARPS - 1);
         }
-        last = __shfl_sync(PL_FULL, last, 0);
-        if (last) {
-            if (lane == 0) sm.released[s] = 0;
-            pl_mbar_wait(&sm.empty[s], ph);     // complete by now; orders the five warps' reads before the refill
-            if (t + PL_L_STAGES < ntiles) pl_lean_fill(sm, s, t + PL_L_STAGES, W, y, parity);
+        order = __shfl_sync(PL_FULL, order, 0);
+        if (order == 0 && t + PL_L_STAGES < ntiles) {
+            pl_mbar_wait(&sm.empty[s], ph);     // all five warps are done with the tile
+            pl_lean_fill(sm, s, t + PL_L_STAGES, W, y, parity);
         }
         __syncwarp();
     }

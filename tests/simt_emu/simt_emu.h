@@ -294,6 +294,12 @@ static inline void mbar_arrive(const void *bar, unsigned tx_bytes) {
     m.pending--;
     m.tx += tx_bytes;
     progress++;
+    // a phase without bulk copies completes with its last arrival, as on the hardware (phases that wait for
+    // bytes complete when a waiter looks: the bytes land as late as possible)
+    if (m.pending == 0 && m.tx == 0 && m.queued == 0) {
+        m.pending = m.count;
+        m.phase ^= 1u;
+    }
 }
 static inline void bulk_copy(void *dst, const void *src, unsigned n, const void *bar) {
     if (n == 0 || (n & 15u) || ((uintptr_t)dst & 15u) || ((uintptr_t)src & 15u)) {

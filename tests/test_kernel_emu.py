@@ -262,6 +262,11 @@ def test_emu_lean_noise_ties_and_paths(emu, oracle):
     for key in ("bm_lookup", "bm_scan", "bm_fast_update", "bm_general_update", "fixup_replay", "fixup_skipped",
                 "taps_table", "taps_computed"):
         assert after[key] > before[key], key
+    # a band that the byte-range clamp empties collapses onto a value OUTSIDE its bucket (few grey levels, wide
+    # bands): the chosen symbol must then be filed under its own bucket, not under the band's
+    wide = (np.random.default_rng(99).integers(0, 6, (2, 256, 4)) * 51).astype(np.uint8)
+    for s in (126, 120, 100):
+        compare(emu, oracle, [wide], s, 2, False, LEAN)
 
 
 def test_emu_lean_early_bulk_copies(oracle):
