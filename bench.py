@@ -1,20 +1,33 @@
 #!/usr/bin/env python
-"""bench.py - Mpixels/s of the quantise + filter-search hot path at 4K RGBA (BASELINE.json metric).
+"""bench.py - Mpixels/s of the quantise + filter-search hot path (BASELINE.json metric).
 
-A "step" is one pass of the hot path (histogram kernel K1, quantise/filter-search kernel K2, batch
-histogram kernel K3, plus the one NCCL all-reduce of the 256-bin symbol histogram when N > 1) over
-one batch of synthetic 3840x2160 RGBA images (SURVEY 8d generator, seeds 4, 5, ...; BASELINE
-configs[2] replicated over seeds so that the machine is filled - a single image is 5 busy warps).
+A "step" is one pass of the hot path (histogram kernel K1, quantise / filter-search kernel K2, batch
+histogram kernel K3, plus the library's NCCL all-reduce of the 256-bin symbol histogram when N > 1) over
+one batch of images.  --config picks the workload; every BASELINE.json config has one:
+
+  (default) 3s  the metric's configuration, saturated: IMAGES x synthetic 3840x2160 RGBA per GPU
+            (SURVEY 8d generator, seeds 4, 5, ...; BASELINE configs[2] replicated over seeds so that the
+            machine is filled - one image is five dependent chains).  Weak scaling.
+  1         suite/david.png -s19 -b2, one image (BASELINE configs[0]; pixels from tests/golden/fixtures.npz)
+  2         suite/lena.png 512x512 -s20, one image (configs[1])
+  3         one synthetic 3840x2160 RGBA image, --strength 0/20/40/85 (configs[2], as the reference's command
+            line would run it: one image per call)
+  4         1024 synthetic 1920x1080 RGBA images in total, sharded over the GPUs (configs[3]); strong scaling
+  5         64 synthetic 8192x8192 RGBA images in total, sharded over the GPUs (configs[4]); strong scaling
 
   value     whole-job Mpx/s with the batch resident in HBM, CUDA events, max over ranks
-  e2e       the same through the C-ABI host-buffer call pngloss_b200_optimize_batch: pinned host
-            buffers, H2D + kernels + D2H inside the timed region
-  roofline  K2 (dominant kernel): algorithmic 8 B/px (4 read + 4 write) / K2's CUDA-event duration
-            against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
-  cpu_baseline  the reference's own C code (oracle/_ref, compiled from the unmodified sources) on all
-            host cores over a bounded sample of the same workload
+  e2e       the same through the C-ABI host-buffer calls (pngloss_b200_submit / _wait, or the reference's own
+            entry point optimize_with_rows for the one-image configs): pinned host buffers, H2D + kernels +
+            D2H inside the timed region
+  roofline  K2 (dominant kernel): algorithmic 8 B/px (4 read + 4 write) / K2's CUDA-event duration against
+            the measured HBM copy bandwidth (MEASURED_PEAKS.json); roofline_k1 likewise (4 B/px)
+  latency_bound  what actually bounds K2: dependent pixel steps per image, SM cycles per step, chains in flight
+  cpu_baseline   the reference's own C code (oracle/_ref, compiled from the unmodified sources) on the host
+            cores over a bounded sample of the same workload
 
---impl reference runs only that CPU arm, as the comparison line the driver asks for.
+Multi-GPU runs (torchrun launches one process per GPU) do not import torch: the ranks meet through the
+library's own NCCL communicator (pngloss_b200_comm_*), the id travels through a file in /tmp.
+--impl reference runs only the CPU arm, as the comparison line the driver asks for.
 """
 import argparse
 import json
@@ -33,6 +46,7 @@ METRIC = "Mpixels/s quantize+filter-search @4K RGBA"
 UNIT = "Mpx/s"
 K2_BYTES_PER_PX = 8.0    # DESIGN.md / SURVEY 8d: 4 B read + 4 B written per pixel
 K1_BYTES_PER_PX = 4.0
+L2_BYTES = 126e6
 
 
 def parse_args():
@@ -41,24 +55,54 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--images", type=int, default=2368,
-                    help="images per GPU per step (default: 16 per SM, two CTAs of 8 images; falls back to "
-                         "half if the device cannot hold them)")
-    ap.add_argument("--width", type=int, default=3840)
-    ap.add_argument("--height", type=int, default=2160)
-    ap.add_argument("--strength", type=int, default=20)
+    ap.add_argument("--config", default="3s", choices=["1", "2", "3", "3s", "4", "5"],
+                    help="BASELINE.json config (see the module docstring); default 3s = the metric's config, saturated")
+    ap.add_argument("--images", type=int, default=0,
+                    help="3s: images per GPU per step (default 3552 = 24 per SM, three CTAs of 8 images); "
+                         "4 / 5: total images of the job (default 1024 / 64)")
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--strength", type=int, default=-1)
     ap.add_argument("--bleed", type=int, default=2)
     ap.add_argument("--lanes", type=int, default=0, help="lanes per channel of K2 (0 = library default)")
     ap.add_argument("--bm", type=int, default=-1,
                     help="K2 candidate choice: 1 bucket maxima, 0 scan only, -1 library default")
+    ap.add_argument("--lean", type=int, default=-1, help="K2 large-batch kernel: 1/-1 on where it applies, 0 off")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows per core of the CPU sample (0 = auto)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    spec = {
+        "3s": dict(w=3840, h=2160, strength=20, per_gpu=3552, total=0, scaling="weak", source="synth", seed0=4),
+        "1": dict(w=180, h=215, strength=19, per_gpu=1, total=0, scaling="weak", source="david", seed0=0),
+        "2": dict(w=512, h=512, strength=20, per_gpu=1, total=0, scaling="weak", source="lena", seed0=0),
+        "3": dict(w=3840, h=2160, strength=20, per_gpu=1, total=0, scaling="weak", source="synth", seed0=4),
+        "4": dict(w=1920, h=1080, strength=20, per_gpu=0, total=1024, scaling="strong", source="synth", seed0=100),
+        "5": dict(w=8192, h=8192, strength=20, per_gpu=0, total=64, scaling="strong", source="synth", seed0=1000),
+    }[a.config]
+    a.width = a.width or spec["w"]
+    a.height = a.height or spec["h"]
+    a.strength = spec["strength"] if a.strength < 0 else a.strength
+    a.scaling = spec["scaling"]
+    a.source = spec["source"]
+    a.seed0 = spec["seed0"]
+    if a.scaling == "strong":
+        a.total = a.images or spec["total"]
+        a.images = 0
+    else:
+        a.total = 0
+        a.images = a.images or spec["per_gpu"]
+    return a
 
 
-def workload_name(a):
-    return (f"{a.images} x synthetic {a.width}x{a.height} RGBA gradient+noise per GPU, "
+def workload_name(a, n_per_gpu):
+    if a.source in ("david", "lena"):
+        return (f"suite/{a.source}.png {a.width}x{a.height} (decoded RGBA from tests/golden/fixtures.npz), "
+                f"one image, strength {a.strength}, bleed {a.bleed}")
+    if a.scaling == "strong":
+        return (f"{a.total} x synthetic {a.width}x{a.height} RGBA gradient+noise in total, sharded over the GPUs, "
+                f"strength {a.strength}, bleed {a.bleed}")
+    return (f"{n_per_gpu} x synthetic {a.width}x{a.height} RGBA gradient+noise per GPU, "
             f"strength {a.strength}, bleed {a.bleed}")
 
 
@@ -70,32 +114,34 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(a):
+def ncu_traffic(a, n):
     """dram bytes per launch from the committed ncu capture (profiles/k2_traffic.json), reported only
     when that capture was taken on the workload being benchmarked."""
     try:
         with open(os.path.join(ROOT, "profiles", "k2_traffic.json")) as f:
             t = json.load(f)
         w = t["workload"]
-        if (w["images_per_gpu"], w["width"], w["height"], w["strength"]) == (a.images, a.width, a.height,
-                                                                           a.strength):
+        if (w["images_per_gpu"], w["width"], w["height"], w["strength"]) == (n, a.width, a.height, a.strength):
             return t
     except Exception:
         pass
     return None
 
 
-# ---- reference CPU arm ---------------------------------------------------------------------------------
-def cpu_reference_run(a, seconds_hint=12.0, rows=0):
-    """Times the reference C path on every host core at once: one strip of the 4K workload per core
-    (the reference is single-threaded and re-entrant; images are independent)."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import ctypes
+def fixture_image(name):
+    z = np.load(os.path.join(ROOT, "tests", "golden", "fixtures.npz"))
+    return np.ascontiguousarray(z[name])
 
+
+# ---- reference CPU arm ---------------------------------------------------------------------------------
+def cpu_reference_run(a, seconds_hint=12.0, rows=0, cores=None):
+    """Times the reference C path on host cores: one strip (or one copy of the image, for the small suite
+    images) per core, all at once (the reference is single-threaded and re-entrant; images are independent)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
     from checkers import Oracle, Reference, have_reference
     from checkers import row_pointers
     oracle = Oracle()
-    cores = os.cpu_count() or 1
+    cores = cores or os.cpu_count() or 1
     if have_reference():
         kind, ref = "reference", Reference()
 
@@ -111,14 +157,22 @@ def cpu_reference_run(a, seconds_hint=12.0, rows=0):
             rf = np.zeros(h, np.uint8)
             oracle.lib.oracle_optimize_with_rows(row_pointers(img), w, h, rf.ctypes.data, a.strength,
                                                  a.bleed, None)
-    # ~0.45 Mpx/s/core on this class of host: size the strip for about seconds_hint of work per core
-    if rows <= 0:
-        rows = int(max(16, min(a.height, 0.45e6 * seconds_hint / a.width)))
-    full = oracle.synth(a.width, a.height, 4)
-    strips = []
-    for c in range(cores):
-        y0 = (c * rows) % max(1, a.height - rows + 1)
-        strips.append(np.ascontiguousarray(full[y0:y0 + rows]).copy())
+    if a.source in ("david", "lena"):
+        full = fixture_image(a.source)
+        strips = [full.copy() for _ in range(cores)]
+        what = f"{cores} copies of the whole image, one per core"
+    else:
+        # ~0.45 Mpx/s/core on this class of host: size the strip for about seconds_hint of work per core
+        if rows <= 0:
+            rows = int(max(16, min(a.height, 0.45e6 * seconds_hint / a.width)))
+        gen_h = min(a.height, 2160)     # strips come from the top rows of the seed-`seed0` image
+        full = oracle.synth(a.width, gen_h, a.seed0)
+        strips = []
+        for c in range(cores):
+            y0 = (c * rows) % max(1, gen_h - rows + 1)
+            strips.append(np.ascontiguousarray(full[y0:y0 + rows]).copy())
+        what = (f"{cores} strips of {a.width}x{rows} (rows of the seed-{a.seed0} {a.width}x{a.height} image), "
+                f"one per core")
     threads = [threading.Thread(target=one, args=(s,)) for s in strips]   # ctypes drops the GIL
     t0 = time.perf_counter()
     for t in threads:
@@ -128,12 +182,17 @@ def cpu_reference_run(a, seconds_hint=12.0, rows=0):
     dt = time.perf_counter() - t0
     px = sum(s.shape[0] * s.shape[1] for s in strips)
     return dict(value=px / dt / 1e6, unit=UNIT, cores=cores, kind=kind, seconds=dt,
-                sample=f"{cores} strips of {a.width}x{rows} (rows of the seed-4 4K image), one per core, "
-                       f"strength {a.strength} bleed {a.bleed}, optimize_with_rows only")
+                sample=f"{what}, strength {a.strength} bleed {a.bleed}, optimize_with_rows only")
+
+
+def config_keys(a, n_per_gpu):
+    return {"workload": workload_name(a, n_per_gpu), "baseline_config": a.config, "images_per_gpu": n_per_gpu,
+            "width": a.width, "height": a.height, "strength": a.strength, "bleed": a.bleed}
 
 
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     for _ in range(a.warmup):
@@ -144,12 +203,14 @@ def run_reference_arm(a):
         vals.append(last["value"])
         secs.append(last["seconds"])
     value = float(np.mean(vals))
+    n_per_gpu = a.images if a.scaling == "weak" else a.total // max(1, world)
+    cfg = config_keys(a, n_per_gpu)
+    cfg["note"] = "CPU arm: every step times a bounded sample of this workload on all host cores"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-        "data": "synthetic", "config": {"workload": workload_name(a), "note":
-                                        "CPU arm: bounded sample of the workload per step"},
+        "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic" if a.source == "synth" else "suite image", "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": last["kind"],
                          "sample": last["sample"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -201,6 +262,34 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+# ---- rendezvous of the ranks without torch ----------------------------------------------------------------------
+def exchange_comm_id(rank, world):
+    """Rank 0 creates the NCCL id and publishes it through a file in /tmp (one node, torchrun contract); the
+    other ranks pick it up.  Files older than this process are leftovers of earlier runs and are ignored."""
+    import pngloss_b200
+    tag = f"{os.environ.get('MASTER_PORT', '0')}_{os.environ.get('TORCHELASTIC_RUN_ID', 'none')}"
+    path = f"/tmp/pngloss_b200_comm_{tag}.id"
+    started = time.time() - 120.0        # every rank of one launch starts within two minutes of rank 0
+    if rank == 0:
+        uid = pngloss_b200.comm_unique_id()
+        tmp = path + f".{os.getpid()}"
+        with open(tmp, "wb") as f:
+            f.write(uid)
+        os.replace(tmp, path)
+        return uid, path
+    deadline = time.time() + 300
+    while time.time() < deadline:
+        try:
+            st = os.stat(path)
+            if st.st_mtime >= started and st.st_size == pngloss_b200.COMM_ID_BYTES:
+                with open(path, "rb") as f:
+                    return f.read(), path
+        except FileNotFoundError:
+            pass
+        time.sleep(0.05)
+    raise RuntimeError("bench: no NCCL id from rank 0")
+
+
 # ---- the B200 arm ---------------------------------------------------------------------------------------------
 def main():
     a = parse_args()
@@ -211,89 +300,115 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    dist = None
-    torch = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import pngloss_b200
     from pngloss_b200.shard import shard_seeds
     ctx = pngloss_b200.Context(local_rank)
+    id_path = None
+    if world > 1:
+        # stale id files of an earlier launch on the same port are older than two minutes or get replaced here
+        uid, id_path = exchange_comm_id(rank, world)
+        ctx.comm_init_rank(world, rank, uid)
+        ctx.barrier()
+        if rank == 0:
+            try:
+                os.remove(id_path)
+            except OSError:
+                pass
+
+    def allmax(v):
+        return float(ctx.comm_allreduce([int(v * 1e3)], "max")[0]) / 1e3 if world > 1 else float(v)
+
+    def allmin_int(v):
+        return int(ctx.comm_allreduce([int(v)], "min")[0]) if world > 1 else int(v)
+
     if a.lanes:
         ctx.set_lanes(a.lanes)
     ctx.set_bucket_maxima(a.bm)
-    n, w, h = a.images, a.width, a.height
-    px_per_step_rank = n * w * h
+    ctx.set_lean(a.lean)
+    w, h = a.width, a.height
+    if a.scaling == "strong":
+        # the job's images are dealt round-robin; every rank gets the same count (the totals divide by 8)
+        n = a.total // world
+        seeds = [a.seed0 + rank + world * i for i in range(n)]
+        job_images = n * world
+    else:
+        n = a.images
+        seeds = None
+        job_images = None
 
-    # the device-resident run keeps inputs and outputs apart (every step re-reads the same inputs):
-    # 2 x 33 MB per 4K image; fall back to half the images where that does not fit
+    # Device-resident batch.  Large batches run in place (half the memory: 24 4K images per SM need 118 GB):
+    # the step then re-creates its inputs on the device first (the synthetic generator kernel, ~0.5 % of the
+    # step, inside the timed region and counted in gpu_launches).  Small batches keep inputs and outputs apart.
+    img_bytes = w * h * 4
+    in_place = a.source == "synth" and n * img_bytes * 2 > 150e9
     while True:
         try:
-            batch = pngloss_b200.Batch(ctx, [w] * n, [h] * n)
+            batch = pngloss_b200.Batch(ctx, [w] * n, [h] * n, in_place=in_place)
             break
         except pngloss_b200.PnglossError as e:
-            if e.code != pngloss_b200.OUT_OF_MEMORY or n <= 8:
+            if e.code != pngloss_b200.OUT_OF_MEMORY or n <= 8 or a.scaling == "strong":
                 raise
-            n //= 2
-    if world > 1:                               # same batch on every rank
-        nmin = torch.tensor([n], device=f"cuda:{local_rank}")
-        dist.all_reduce(nmin, op=dist.ReduceOp.MIN)
-        if int(nmin.item()) != n:
-            batch.close()
-            n = int(nmin.item())
-            batch = pngloss_b200.Batch(ctx, [w] * n, [h] * n)
-    a.images = n
+            n = n * 2 // 3
+    nmin = allmin_int(n)
+    if nmin != n:                               # same batch on every rank
+        batch.close()
+        n = nmin
+        batch = pngloss_b200.Batch(ctx, [w] * n, [h] * n, in_place=in_place)
+    if a.scaling == "weak":
+        a.images = n
+        seeds = shard_seeds(rank, world, n) if a.source == "synth" else None
+        if seeds is not None and a.seed0 != 4:
+            seeds = [s - 4 + a.seed0 for s in seeds]
     px_per_step_rank = n * w * h
-    seeds = shard_seeds(rank, world, n)        # distinct images on every rank (shards, not replicas)
-    for i in range(n):
-        batch.synth(i, seeds[i])
-    ctx.sync()
 
-    hist_alias = None
-    if world > 1:
-        # zero-copy torch view of the library's device-side batch histogram for the NCCL all-reduce
-        class _Alias:
-            __cuda_array_interface__ = {"shape": (256,), "typestr": "<i8", "version": 2,
-                                        "data": (batch.histogram_device_ptr(), False)}
-        hist_alias = torch.as_tensor(_Alias(), device=f"cuda:{local_rank}")
+    host_img = fixture_image(a.source) if a.source in ("david", "lena") else None
+
+    def load_inputs():
+        if host_img is not None:
+            for i in range(n):
+                batch.upload(i, host_img)
+        else:
+            for i in range(n):
+                batch.synth(i, seeds[i])
+
+    load_inputs()
+    ctx.sync()
+    small = n * img_bytes < 4 * L2_BYTES        # inputs that could stay in L2 between steps: flush it
+    launches_per_step = [0]
 
     def step():
+        extra = 0
+        if in_place:
+            load_inputs()                       # restore the inputs the previous step overwrote
+            extra += n
+        if small:
+            ctx.flush_l2()                      # a memset, not one of our kernels: not counted
         batch.run(a.strength, a.bleed)
         if world > 1:
-            ctx.sync()                          # library stream -> NCCL stream
-            dist.all_reduce(hist_alias)         # the one collective of the path: 256 x u64 symbol counts
-            torch.cuda.synchronize()
+            batch.allreduce_histogram()         # the one collective of the path: 256 x u64 symbol counts
+        launches_per_step[0] = extra + 3
 
     def fence():
         ctx.sync()
-        if world > 1:
-            torch.cuda.synchronize()
-            dist.barrier()
+        ctx.barrier()
 
     for _ in range(a.warmup):
         step()
     fence()
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    k1_ms, k2_ms, k3_ms = [], [], []
+    k1_ms, k2_ms, k3_ms, run_ms = [], [], [], []
     fence()
     ctx.timer_start()
     t_wall = time.perf_counter()
     for _ in range(a.steps):
-        tw0 = time.perf_counter()
         step()
-        tw1 = time.perf_counter()
         batch.finish()
-        tw2 = time.perf_counter()
         t = batch.timings()
-        if os.environ.get("PNGLOSS_BENCH_TRACE"):
-            print(f"[trace] enqueue {tw1 - tw0:.3f}s finish {tw2 - tw1:.3f}s run_ms {t['run_ms']:.1f}",
-                  file=sys.stderr, flush=True)
         k1_ms.append(t["k1_hist_ms"])
         k2_ms.append(t["k2_quantize_ms"])
         k3_ms.append(t["k3_batch_hist_ms"])
+        run_ms.append(t["run_ms"])
     ms = ctx.timer_stop()
     fence()
     wall_ms = (time.perf_counter() - t_wall) * 1e3
@@ -301,127 +416,57 @@ def main():
     st, bpp, retried = batch.finish()
     assert (st == 0).all(), "quantise kernel reported a failed image"
     info = batch.launch_info()
-    global_hist_sum = int(batch.histogram().sum()) if world == 1 else int(hist_alias.sum().item())
+    global_hist_sum = int(batch.histogram().sum())
 
-    if world > 1:
-        tmax = torch.tensor([ms], device=f"cuda:{local_rank}")
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms = float(tmax.item())
-    ms_per_step = ms / a.steps
+    if small:
+        # the bracket contains the L2 flushes; the step is the sum of its kernels' own events
+        ms_per_step = allmax(float(np.mean(run_ms)))
+    else:
+        ms_per_step = allmax(ms) / a.steps
     value = world * px_per_step_rank / (ms_per_step * 1e-3) / 1e6
 
-    # ---- end to end through the host-buffer C-ABI call --------------------------------------------------
+    # ---- end to end through the host-buffer C-ABI calls -------------------------------------------------
     e2e = None
     if not a.no_e2e:
-        batch.close()                           # give the HBM back; optimize_batch allocates its own
-        # Host memory: one pinned input buffer that no step modifies and one pinned output buffer, within
-        # 60 % of what the host has free.  When that cannot hold the step's images twice, the output
-        # buffer stays complete and the input buffer holds fewer DISTINCT images: image i is uploaded from
-        # input slot i % m.  Every step still uploads and downloads every image (the byte counts below are
-        # what crosses PCIe); only the content of some uploads repeats.
-        img_bytes = w * h * 4
-        n2, m = n, n
-        try:
-            avail = int([ln for ln in open("/proc/meminfo") if ln.startswith("MemAvailable")][0].split()[1]) * 1024
-            budget = int(0.6 * avail / world / img_bytes)      # images the two buffers may hold together
-            n2 = max(1, min(n, 2 * budget // 3))               # at least half of the inputs are distinct
-            m = max(1, min(n2, budget - n2))
-        except Exception:
-            pass
-        if world > 1:
-            nmin = torch.tensor([n2, m], device=f"cuda:{local_rank}")
-            dist.all_reduce(nmin, op=dist.ReduceOp.MIN)
-            n2, m = int(nmin[0].item()), int(nmin[1].item())
-        # The steps go through the asynchronous call (pngloss_b200_submit / _wait), two in flight, so that
-        # the upload of step k+1 and the download of step k-1 run under the kernels of step k.  (A step's
-        # results are complete when its wait returns; the next step's download overwrites them afterwards.)
-        while True:
-            src = None
-            try:
-                src = ctx.pinned_empty((m, h, w, 4))
-                dst = [ctx.pinned_empty((n2, h, w, 4))] * 2
-                ok = 1
-            except pngloss_b200.PnglossError:
-                if src is not None:
-                    ctx.free_pinned(src)
-                ok = 0
-            if world > 1:                           # all ranks shrink together
-                flag = torch.tensor([ok], device=f"cuda:{local_rank}")
-                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-                if ok and not int(flag.item()):
-                    ctx.free_pinned(src)
-                    ctx.free_pinned(dst[0])
-                ok = int(flag.item())
-            if ok:
-                break
-            if n2 <= 8:
-                raise RuntimeError("bench: no pinned host memory for the end-to-end part")
-            n2, m = n2 // 2, max(1, m // 2)
-        b2 = pngloss_b200.Batch(ctx, [w] * m, [h] * m, in_place=True)
-        for i in range(m):
-            b2.synth(i, seeds[i])
-            b2.download_input(i, src[i])
-        ctx.sync()
-        b2.close()
-        filters = [[np.zeros(h, np.uint8) for _ in range(n2)] for _ in range(2)]
-        imgs = [src[i % m] for i in range(n2)]
-        outs = [[dst[k][i] for i in range(n2)] for k in range(2)]
-
-        def run_steps(count):
-            jobs = []
-            for it in range(count):
-                jobs.append(ctx.submit(imgs, filters[it % 2], a.strength, a.bleed, outputs=outs[it % 2]))
-                if len(jobs) == 2:
-                    res = jobs.pop(0).wait()
-                    assert all(r["status"] == 0 for r in res)
-            while jobs:
-                res = jobs.pop(0).wait()
-                assert all(r["status"] == 0 for r in res)
-
-        run_steps(2)                            # the device is warm; this creates both device batches of the pipeline
-        if world > 1:
-            dist.barrier()
-        ctx.timer_start()                       # CUDA events that cover the upload, compute and download streams
-        tw = time.perf_counter()
-        run_steps(a.steps)
-        e_total = ctx.timer_stop()
-        e_wall = (time.perf_counter() - tw) * 1e3
-        e_step = e_total / a.steps
-        if world > 1:
-            tmax = torch.tensor([e_step], device=f"cuda:{local_rank}")
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            e_step = float(tmax.item())
-        e2e = {"value": world * n2 * w * h / (e_step * 1e-3) / 1e6, "unit": UNIT,
-               "h2d_bytes_per_step": int(n2 * img_bytes), "d2h_bytes_per_step": int(n2 * (img_bytes + h)),
-               "ms_per_step": e_step, "wall_ms_per_step": e_wall / a.steps, "images_per_gpu": n2,
-               "distinct_host_inputs_per_gpu": m,
-               "api": "pngloss_b200_submit / pngloss_b200_wait, two steps in flight (pinned host input and "
-                      "output buffers; every step uploads its input and downloads its result)"}
-        ctx.free_pinned(src)
-        ctx.free_pinned(dst[0])
+        batch.close()                           # give the HBM back; the host-buffer calls allocate their own
+        batch = None
+        if n == 1:
+            e2e = e2e_single_image(a, ctx, pngloss_b200, host_img, seeds, w, h)
+        else:
+            e2e = e2e_job_api(a, ctx, pngloss_b200, seeds, n, w, h, world, allmax, allmin_int)
 
     if rank == 0:
         peak, peak_src = measured_peak()
         k2_s = float(np.mean(k2_ms)) * 1e-3
         k1_s = float(np.mean(k1_ms)) * 1e-3
         achieved = K2_BYTES_PER_PX * px_per_step_rank / k2_s / 1e9
-        tr = ncu_traffic(a)
+        tr = ncu_traffic(a, n)
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        images_per_cta = max(1, info["images_per_cta"])
+        cfg = config_keys(a, n)
+        cfg.update({
+            "l2": ("flushed between steps (512 MB memset); the step time is the sum of its kernels' CUDA events"
+                   if small else f"inputs {n * img_bytes / 1e9:.1f} GB per GPU >> 126 MB L2, no flush needed"),
+            "device_batch": ("in place; the step re-creates its inputs with the generator kernel first"
+                             if in_place else "separate input and output buffers"),
+            "k2_kernel": "pl_k2_lean" if info.get("lean") else "pl_k2_quantize",
+            "k2_lanes_per_channel": 8 // images_per_cta,
+            "k2_candidate_choice": "bucket maxima" if info["bucket_maxima"] else "scan",
+            "k2_ctas": info["k2_ctas"], "k2_smem_bytes": info["k2_smem_bytes"],
+            "collective": ("nccl all_reduce 256 x u64 per step, issued by the library "
+                           "(pngloss_b200_batch_allreduce_histogram)") if world > 1 else "none (1 GPU)",
+            "wall_ms_per_step": wall_ms / a.steps})
+        if job_images:
+            cfg["images_total"] = job_images
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": workload_name(a), "images_per_gpu": n, "width": w, "height": h,
-                       "strength": a.strength, "bleed": a.bleed,
-                       "l2": f"inputs {n * w * h * 4 / 1e9:.1f} GB per GPU >> 126 MB L2, no flush needed",
-                       "k2_lanes_per_channel": 8 // info["images_per_cta"],
-                       "k2_candidate_choice": "bucket maxima" if info["bucket_maxima"] else "scan",
-                       "k2_ctas": info["k2_ctas"], "k2_smem_bytes": info["k2_smem_bytes"],
-                       "collective": "nccl all_reduce 256 x u64 per step" if world > 1 else "none (1 GPU)",
-                       "wall_ms_per_step": wall_ms / a.steps},
+            "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": a.scaling,
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic" if a.source == "synth" else "suite image",
+            "config": cfg,
             "clocks": clocks,
             "e2e": e2e,
-            "gpu_launches": int(info["launches"]) * a.steps,
-            "roofline": {"bound": "hbm", "kernel": "pl_k2_quantize", "achieved": achieved, "peak": peak,
+            "gpu_launches": int(launches_per_step[0]) * a.steps,
+            "roofline": {"bound": "hbm", "kernel": cfg["k2_kernel"], "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          "traffic": tr.get("k2_dram_bytes_per_launch") if tr else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_px": K2_BYTES_PER_PX,
@@ -433,20 +478,166 @@ def main():
                             "unit": "GB/s", "frac": K1_BYTES_PER_PX * px_per_step_rank / k1_s / 1e9 / peak,
                             "traffic": tr.get("k1_dram_bytes_per_launch") if tr else None,
                             "kernel_ms": k1_s * 1e3},
+            # What bounds K2: every image is w*h dependent pixel steps per filter candidate;
+            # a step costs `cycles_per_pixel_step` SM cycles of latency, and images * 5 such chains run at once.
+            "latency_bound": latency_bound(info, n, w, h, k2_s, sm_mhz),
             "kernel_ms": {"k1_orig_hist": float(np.mean(k1_ms)), "k2_quantize": float(np.mean(k2_ms)),
                           "k3_batch_hist": float(np.mean(k3_ms))},
             "checks": {"symbols_counted": global_hist_sum,
-                       "symbols_expected": world * px_per_step_rank * 4,
+                       "symbols_expected": world * px_per_step_rank * int(bpp[0]),
                        "retried_rows": int(retried.sum())},
         }
         if world == 1 and not a.no_cpu:
             cb = cpu_reference_run(a, rows=a.cpu_rows)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            cb1 = cpu_reference_run(a, seconds_hint=4.0, rows=a.cpu_rows, cores=1)
+            line["cpu_baseline"]["one_core"] = {"value": cb1["value"], "unit": UNIT, "sample": cb1["sample"]}
         print(json.dumps(line), flush=True)
+    if batch is not None:
+        batch.close()
+    ctx.barrier()
     ctx.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+
+
+def latency_bound(info, n, w, h, k2_s, sm_mhz):
+    """What bounds K2.  Every image is w*h dependent pixel steps per filter candidate; all
+    images resident on the SMs advance together, so K2's time = waves x (w*h) x the wall-clock cost of one step,
+    and throughput = images in flight / that cost."""
+    ctas_per_sm = 3 if info.get("lean") else {8: 2, 4: 3}.get(info["images_per_cta"], 4)
+    resident = 148 * ctas_per_sm
+    waves = max(1, -(-info["k2_ctas"] // resident))
+    in_flight = min(n, resident * info["images_per_cta"])
+    cycles = k2_s * sm_mhz * 1e6 / (w * h * waves)
+    return {"pixel_steps_per_image": w * h, "images_in_flight": in_flight, "chains_in_flight": in_flight * 5,
+            "waves": waves, "cycles_per_pixel_step": cycles, "sm_mhz": sm_mhz,
+            "mpx_s_per_image": sm_mhz / cycles,
+            "bound_mpx_s": in_flight * sm_mhz / cycles,
+            "note": "cycles_per_pixel_step = K2 time x SM clock / (pixels of one image x waves): the latency of one "
+                    "step of an image's five dependent chains at this occupancy; bound_mpx_s = images in flight x "
+                    "SM clock / cycles_per_pixel_step.  Warp instructions and issue-slot utilisation per step: "
+                    "profiles/ (ncu)"}
+
+
+def e2e_single_image(a, ctx, pngloss_b200, host_img, seeds, w, h):
+    """One image per call through the reference's own entry point, optimize_with_rows (src/pngloss.c:266):
+    host buffer in, quantised in place, row filters out; upload, kernels and download inside the timed call."""
+    if host_img is None:
+        b2 = pngloss_b200.Batch(ctx, [w], [h], in_place=True)
+        b2.synth(0, seeds[0])
+        src = ctx.pinned_empty((h, w, 4))
+        b2.download_input(0, src)
+        ctx.sync()
+        b2.close()
+    else:
+        src = ctx.pinned_empty((h, w, 4))
+        src[:] = host_img
+    work = ctx.pinned_empty((h, w, 4))
+    rf = np.zeros(h, np.uint8)
+    times = []
+    for it in range(a.warmup + a.steps):
+        work[:] = src                           # the call quantises in place: restore the input (not timed)
+        ctx.flush_l2()
+        ctx.sync()
+        t0 = time.perf_counter()
+        rc = pngloss_b200.optimize_with_rows(work, rf, False, a.strength, a.bleed)
+        dt = time.perf_counter() - t0
+        assert rc == 0
+        if it >= a.warmup:
+            times.append(dt)
+    e_step = float(np.mean(times)) * 1e3
+    out = {"value": w * h / (e_step * 1e-3) / 1e6, "unit": UNIT,
+           "h2d_bytes_per_step": int(w * h * 4), "d2h_bytes_per_step": int(w * h * 4 + h),
+           "ms_per_step": e_step, "images_per_gpu": 1,
+           "api": "optimize_with_rows (the reference's own entry point, one image per call; host wall clock "
+                  "around the blocking call, pinned host buffer)"}
+    ctx.free_pinned(src)
+    ctx.free_pinned(work)
+    return out
+
+
+def e2e_job_api(a, ctx, pngloss_b200, seeds, n, w, h, world, allmax, allmin_int):
+    """The step through pngloss_b200_submit / _wait with host buffers.
+
+    Saturated config (3s): a step's images do not fit the device twice, so the step is cut into jobs of 296
+    images (37 CTAs of the large-batch kernel) and the context runs as a pipeline (pngloss_b200_ctx_set_pipeline):
+    every job computes on its own stream, about twelve jobs share the SMs at any time (24 images per SM), and as
+    one job's CTAs finish the next job's take their places while its results go back over PCIe and the job
+    after it is uploaded.  Other configs: one or two jobs per step, two in flight.
+
+    Host buffers are rings whose size does not depend on the number of ranks: image i is uploaded from input
+    slot i % slots_in (inputs are never modified) and job j's results land in output ring segment j % 4 (a
+    consumer such as the PNG encoder would have taken them before the segment comes round again).  Every step
+    uploads and downloads every image; the byte counts below are what crosses PCIe."""
+    img_bytes = w * h * 4
+    pipeline = a.config == "3s" and n >= 1184
+    if pipeline:
+        per_job = 296
+        jobs_per_step = -(-n // per_job)
+        in_flight = min(jobs_per_step, 12) + 3
+        ctx.set_lanes(1)
+        ctx.set_pipeline(in_flight)
+        out_segments = 4
+    else:
+        per_job = n if n * img_bytes <= 60e9 else -(-n // 2)
+        jobs_per_step = -(-n // per_job)
+        in_flight = 2
+        out_segments = 2
+    slots_in = allmin_int(min(n, max(per_job, int(20e9 // img_bytes))))
+    src = ctx.pinned_empty((slots_in, h, w, 4))
+    dst = ctx.pinned_empty((out_segments * per_job, h, w, 4))
+    gen = min(slots_in, 64)
+    b2 = pngloss_b200.Batch(ctx, [w] * gen, [h] * gen, in_place=True)
+    for base in range(0, slots_in, gen):
+        cnt = min(gen, slots_in - base)
+        for i in range(cnt):
+            b2.synth(i, seeds[(base + i) % len(seeds)])
+            b2.download_input(i, src[base + i])
+        ctx.sync()
+    b2.close()
+    filters = [np.zeros(h, np.uint8) for _ in range(out_segments * per_job)]
+    state = {"job": 0}
+
+    def job_args(j):
+        idx = list(range(j * per_job, min(n, (j + 1) * per_job)))
+        seg = (state["job"] % out_segments) * per_job
+        state["job"] += 1
+        return ([src[i % slots_in] for i in idx], [filters[seg + k] for k in range(len(idx))],
+                [dst[seg + k] for k in range(len(idx))])
+
+    def run_steps(count):
+        inflight = []
+        for _ in range(count):
+            for j in range(jobs_per_step):
+                ins, rfs, outs = job_args(j)
+                inflight.append(ctx.submit(ins, rfs, a.strength, a.bleed, outputs=outs))
+                if len(inflight) >= in_flight:
+                    res = inflight.pop(0).wait()
+                    assert all(r["status"] == 0 for r in res)
+        while inflight:
+            res = inflight.pop(0).wait()
+            assert all(r["status"] == 0 for r in res)
+
+    run_steps(1)                                # creates the device batches of the pipeline
+    ctx.barrier()
+    ctx.timer_start()                           # CUDA events that cover the upload, compute and download streams
+    tw = time.perf_counter()
+    run_steps(a.steps)
+    e_total = ctx.timer_stop()
+    e_wall = (time.perf_counter() - tw) * 1e3
+    e_step = allmax(e_total / a.steps)
+    out = {"value": world * n * w * h / (e_step * 1e-3) / 1e6, "unit": UNIT,
+           "h2d_bytes_per_step": int(n * img_bytes), "d2h_bytes_per_step": int(n * (img_bytes + h)),
+           "ms_per_step": e_step, "wall_ms_per_step": e_wall / a.steps, "images_per_gpu": n,
+           "jobs_per_step": jobs_per_step, "images_per_job": per_job, "jobs_in_flight": in_flight,
+           "host_input_ring_images": slots_in, "host_output_ring_images": out_segments * per_job,
+           "api": ("pngloss_b200_submit / pngloss_b200_wait, pipeline of %d jobs in flight on their own streams "
+                   "(pngloss_b200_ctx_set_pipeline)" % in_flight) if pipeline else
+                  "pngloss_b200_submit / pngloss_b200_wait, two jobs in flight",
+           "note": "pinned host rings; every step uploads all its inputs and downloads all its results; the timed "
+                   "region starts and ends with an idle device (pipeline fill and drain included)"}
+    ctx.free_pinned(src)
+    ctx.free_pinned(dst)
+    return out
 
 
 if __name__ == "__main__":

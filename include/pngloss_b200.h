@@ -130,6 +130,13 @@ int pngloss_b200_optimize_batch(pngloss_b200_ctx *ctx, pngloss_b200_image *image
  * are not asynchronous).  `images` and the buffers it points to must stay valid until wait returns.
  * When the device cannot hold another batch, submit first waits for the oldest job in flight. */
 typedef struct pngloss_b200_job pngloss_b200_job;
+/* How many jobs the context keeps on the device at once (default 2: the copies of one job overlap the kernels of
+ * the other, kernels run back to back - right when every job fills the GPU by itself).  With more than 2 every
+ * job also computes on a stream of its own, so that many small jobs share the SMs: as one job's CTAs finish,
+ * the next job's CTAs take their places, and uploads, kernels and downloads of different jobs overlap
+ * continuously - the streaming set-up for inputs that together exceed the device memory.  Call before the first
+ * submit. */
+int pngloss_b200_ctx_set_pipeline(pngloss_b200_ctx *ctx, int jobs_in_flight);
 int pngloss_b200_submit(pngloss_b200_ctx *ctx, pngloss_b200_image *images, size_t n, unsigned strength,
                         long bleed, pngloss_b200_job **job);
 int pngloss_b200_wait(pngloss_b200_job *job);
@@ -211,6 +218,11 @@ int pngloss_b200_batch_allreduce_histogram(pngloss_b200_batch *b);
 /* Up to 256 host values reduced over the ranks, blocking (a barrier when the result is ignored).
  * op: 0 sum, 1 max, 2 min. */
 int pngloss_b200_comm_allreduce_u64(pngloss_b200_ctx *ctx, uint64_t *values, size_t n, int op);
+
+/* Symbol counts (256 x u64) of every image this context's host-buffer calls (optimize_batch, submit / wait) have
+ * finished so far.  across_ranks != 0 and a communicator on the context: summed over all ranks by the NCCL
+ * all-reduce (blocking; every rank must call). */
+int pngloss_b200_ctx_symbol_histogram(pngloss_b200_ctx *ctx, uint64_t out256[256], int across_ranks);
 
 /* Benchmark helper: overwrite a buffer larger than the L2 cache on the context's stream. */
 int pngloss_b200_ctx_flush_l2(pngloss_b200_ctx *ctx);

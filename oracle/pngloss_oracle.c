@@ -116,6 +116,19 @@ static void candidate_assign(candidate *to, const candidate *from, const job *j)
 }
 
 /* reference src/optimize_state.c:390-467 (the live "sierra dithering" block) */
+/* Test instrumentation: how often a store into an int16 error cell did not fit 16 bits and wrapped (the reference
+ * relies on that narrowing, src/color_delta.h:6; tests use the count to prove that a vector exercises it). */
+static uint64_t g_int16_wraps;
+uint64_t oracle_int16_wraps(int reset) {
+    const uint64_t n = g_int16_wraps;
+    if (reset) g_int16_wraps = 0;
+    return n;
+}
+static inline int16_t narrow16(long v) {
+    if (v < -32768 || v > 32767) g_int16_wraps++;
+    return (int16_t)v;
+}
+
 static void diffuse(candidate *c, const job *j, uint32_t x, const int16_t diff[4]) {
     const size_t ew = (size_t)j->width + ERR_PAD;
     int16_t *r0 = c->err + (0 * ew + x) * 4;
@@ -127,26 +140,26 @@ static void diffuse(candidate *c, const job *j, uint32_t x, const int16_t diff[4
 
         long twos = d / 16;
         d -= twos * 4;
-        r1[0 * 4 + lane] = (int16_t)(r1[0 * 4 + lane] + twos);
-        r1[4 * 4 + lane] = (int16_t)(r1[4 * 4 + lane] + twos);
-        r2[1 * 4 + lane] = (int16_t)(r2[1 * 4 + lane] + twos);
-        r2[3 * 4 + lane] = (int16_t)(r2[3 * 4 + lane] + twos);
+        r1[0 * 4 + lane] = narrow16(r1[0 * 4 + lane] + twos);
+        r1[4 * 4 + lane] = narrow16(r1[4 * 4 + lane] + twos);
+        r2[1 * 4 + lane] = narrow16(r2[1 * 4 + lane] + twos);
+        r2[3 * 4 + lane] = narrow16(r2[3 * 4 + lane] + twos);
 
         long threes = d / 8;
         d -= threes * 2;
-        r0[4 * 4 + lane] = (int16_t)(r0[4 * 4 + lane] + threes);
-        r2[2 * 4 + lane] = (int16_t)(r2[2 * 4 + lane] + threes);
+        r0[4 * 4 + lane] = narrow16(r0[4 * 4 + lane] + threes);
+        r2[2 * 4 + lane] = narrow16(r2[2 * 4 + lane] + threes);
 
         long fours = d * 2 / 9;
         d -= fours * 2;
-        r1[1 * 4 + lane] = (int16_t)(r1[1 * 4 + lane] + fours);
-        r1[3 * 4 + lane] = (int16_t)(r1[3 * 4 + lane] + fours);
+        r1[1 * 4 + lane] = narrow16(r1[1 * 4 + lane] + fours);
+        r1[3 * 4 + lane] = narrow16(r1[3 * 4 + lane] + fours);
 
         long five = d / 2;
         d -= five;
-        r1[2 * 4 + lane] = (int16_t)(r1[2 * 4 + lane] + five);
+        r1[2 * 4 + lane] = narrow16(r1[2 * 4 + lane] + five);
 
-        r0[3 * 4 + lane] = (int16_t)(r0[3 * 4 + lane] + d);
+        r0[3 * 4 + lane] = narrow16(r0[3 * 4 + lane] + d);
     }
 }
 

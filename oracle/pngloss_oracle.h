@@ -62,6 +62,9 @@ void oracle_original_frequency(const uint8_t *pixels, uint32_t width, uint32_t h
 int oracle_adaptive_filter(const uint8_t *above, const uint8_t *row,
                            uint32_t width, uint32_t bytes_per_pixel);
 
+/* Test instrumentation: number of int16 error-cell stores that wrapped since the last reset (not thread safe). */
+uint64_t oracle_int16_wraps(int reset);
+
 /* Stateless synthetic image generator shared by tests and bench. */
 void oracle_synth_rgba(uint8_t *dst, uint32_t width, uint32_t height, uint64_t seed);
 

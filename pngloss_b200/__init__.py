@@ -42,7 +42,7 @@ EXPORTS = [
     "pngloss_b200_batch_download_scanlines",
     "pngloss_b200_comm_unique_id", "pngloss_b200_comm_init_rank", "pngloss_b200_comm_init_all",
     "pngloss_b200_comm_destroy", "pngloss_b200_comm_size", "pngloss_b200_batch_allreduce_histogram",
-    "pngloss_b200_comm_allreduce_u64", "pngloss_b200_ctx_flush_l2",
+    "pngloss_b200_comm_allreduce_u64", "pngloss_b200_ctx_flush_l2", "pngloss_b200_ctx_set_pipeline", "pngloss_b200_ctx_symbol_histogram",
 ]
 
 
@@ -166,6 +166,8 @@ def load_library() -> ctypes.CDLL:
     L.pngloss_b200_batch_allreduce_histogram.argtypes = [vp]
     L.pngloss_b200_comm_allreduce_u64.argtypes = [vp, vp, sz, i32]
     L.pngloss_b200_ctx_flush_l2.argtypes = [vp]
+    L.pngloss_b200_ctx_set_pipeline.argtypes = [vp, i32]
+    L.pngloss_b200_ctx_symbol_histogram.argtypes = [vp, vp, i32]
     _lib = L
     return L
 
@@ -268,6 +270,16 @@ class Context:
     def barrier(self):
         if self.comm_size() > 1:
             self.comm_allreduce([0])
+
+    def symbol_histogram(self, across_ranks: bool = False) -> np.ndarray:
+        """Symbol counts of every image the host-buffer calls of this context finished (NCCL sum over ranks)."""
+        out = np.zeros(256, np.uint64)
+        self._check(self.lib.pngloss_b200_ctx_symbol_histogram(self.handle, out.ctypes.data, int(across_ranks)))
+        return out
+
+    def set_pipeline(self, jobs_in_flight: int):
+        """Device batches the job API keeps at once; > 2: every job computes on its own stream (see the header)."""
+        self._check(self.lib.pngloss_b200_ctx_set_pipeline(self.handle, jobs_in_flight))
 
     def flush_l2(self):
         self._check(self.lib.pngloss_b200_ctx_flush_l2(self.handle))

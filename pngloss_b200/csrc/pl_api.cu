@@ -30,17 +30,22 @@ struct pngloss_b200_ctx {
     cudaStream_t h2d = nullptr, d2h = nullptr;
     std::vector<pngloss_b200_batch *> pool;
     std::vector<pngloss_b200_job *> inflight;   // in submission order
+    size_t max_jobs = 2;                        // device batches the job API keeps (pngloss_b200_ctx_set_pipeline)
+    bool job_streams = false;                   // every pooled batch computes on a stream of its own
     // multi-GPU (pl_comm.cuh): NCCL communicator of this context's device, scratch for small reductions
     void *comm = nullptr;
     int comm_ranks = 0, comm_rank = 0;
     unsigned long long *comm_scratch = nullptr;
+    unsigned long long symbols[256] = {0};      // symbol counts of every image the host-buffer calls finished
     unsigned char *scrub = nullptr;             // pngloss_b200_ctx_flush_l2
     size_t scrub_bytes = 0;
 };
 
 struct pngloss_b200_batch {
     pngloss_b200_ctx *ctx = nullptr;
-    cudaStream_t stream = nullptr;       // the context's stream
+    cudaStream_t stream = nullptr;       // the context's stream, or the batch's own (job pipeline)
+    bool own_stream = false;
+    bool pooled = false;                 // owned by the job API's pool
     size_t n = 0;
     std::vector<uint32_t> w, h;
     std::vector<PlImageDev> himgs;
@@ -56,6 +61,7 @@ struct pngloss_b200_batch {
     unsigned long long *batch_hist = nullptr;
     std::vector<int> hslots;
     uint32_t *hstatus = nullptr;         // pinned: [n][4] status words, copied back asynchronously
+    unsigned long long *hbhist = nullptr; // pinned (tail of the same allocation): the batch histogram, job API
     // row filters of all images, contiguous on the device so that the job API fetches them with one copy
     unsigned char *dfilters = nullptr, *hfilters = nullptr;   // hfilters: pinned staging, allocated on demand
     std::vector<size_t> filt_off;
@@ -173,6 +179,13 @@ extern "C" int pngloss_b200_ctx_set_lean(pngloss_b200_ctx *ctx, int mode) {
     return PNGLOSS_B200_SUCCESS;
 }
 
+extern "C" int pngloss_b200_ctx_set_pipeline(pngloss_b200_ctx *ctx, int jobs_in_flight) {
+    if (!ctx || jobs_in_flight < 1 || jobs_in_flight > 64) return PNGLOSS_B200_INVALID_ARGUMENT;
+    ctx->max_jobs = (size_t)jobs_in_flight;
+    ctx->job_streams = jobs_in_flight > 2;
+    return PNGLOSS_B200_SUCCESS;
+}
+
 extern "C" int pngloss_b200_ctx_set_bucket_maxima(pngloss_b200_ctx *ctx, int mode) {
     if (!ctx || mode < -1 || mode > 1) return PNGLOSS_B200_INVALID_ARGUMENT;
     ctx->bm = mode;
@@ -181,9 +194,16 @@ extern "C" int pngloss_b200_ctx_set_bucket_maxima(pngloss_b200_ctx *ctx, int mod
 
 // The stopwatch events sit on the compute stream; the copy streams of the job API are joined into it
 // first, so that the interval covers everything enqueued on any of the three.
+static std::vector<cudaStream_t> side_streams(pngloss_b200_ctx *ctx) {
+    std::vector<cudaStream_t> v;
+    if (ctx->h2d) v.push_back(ctx->h2d);
+    if (ctx->d2h) v.push_back(ctx->d2h);
+    for (pngloss_b200_batch *b : ctx->pool)
+        if (b->own_stream) v.push_back(b->stream);
+    return v;
+}
 static int join_copy_streams(pngloss_b200_ctx *ctx, cudaEvent_t scratch) {
-    for (cudaStream_t s : {ctx->h2d, ctx->d2h}) {
-        if (!s) continue;
+    for (cudaStream_t s : side_streams(ctx)) {
         PL_CUDA(ctx, cudaEventRecord(scratch, s));
         PL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, scratch, 0));
     }
@@ -195,9 +215,8 @@ extern "C" int pngloss_b200_ctx_timer_start(pngloss_b200_ctx *ctx) {
     PL_CUDA(ctx, cudaSetDevice(ctx->device));
     if (int rc = join_copy_streams(ctx, ctx->t0)) return rc;
     PL_CUDA(ctx, cudaEventRecord(ctx->t0, ctx->stream));
-    // later work on the copy streams must not start before the clock does
-    for (cudaStream_t s : {ctx->h2d, ctx->d2h})
-        if (s) PL_CUDA(ctx, cudaStreamWaitEvent(s, ctx->t0, 0));
+    // later work on the copy / job streams must not start before the clock does
+    for (cudaStream_t s : side_streams(ctx)) PL_CUDA(ctx, cudaStreamWaitEvent(s, ctx->t0, 0));
     return PNGLOSS_B200_SUCCESS;
 }
 
@@ -216,6 +235,8 @@ extern "C" int pngloss_b200_ctx_sync(pngloss_b200_ctx *ctx) {
     PL_CUDA(ctx, cudaSetDevice(ctx->device));
     if (ctx->h2d) PL_CUDA(ctx, cudaStreamSynchronize(ctx->h2d));
     PL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (pngloss_b200_batch *b : ctx->pool)
+        if (b->own_stream) PL_CUDA(ctx, cudaStreamSynchronize(b->stream));
     if (ctx->d2h) PL_CUDA(ctx, cudaStreamSynchronize(ctx->d2h));
     return PNGLOSS_B200_SUCCESS;
 }
@@ -272,12 +293,13 @@ extern "C" int pngloss_b200_batch_create_ex(pngloss_b200_ctx *ctx, size_t n, con
     b->w.assign(widths, widths + n);
     b->h.assign(heights, heights + n);
     b->himgs.resize(n);
-    if (cudaMallocHost((void **)&b->hstatus, n * 4 * sizeof(uint32_t)) != cudaSuccess) {
+    if (cudaMallocHost((void **)&b->hstatus, n * 4 * sizeof(uint32_t) + 256 * sizeof(unsigned long long)) != cudaSuccess) {
         cudaGetLastError();
         delete b;
         return set_err(ctx, PNGLOSS_B200_OUT_OF_MEMORY, "cudaMallocHost(status) failed");
     }
-    memset(b->hstatus, 0, n * 4 * sizeof(uint32_t));
+    memset(b->hstatus, 0, n * 4 * sizeof(uint32_t) + 256 * sizeof(unsigned long long));
+    b->hbhist = (unsigned long long *)(b->hstatus + n * 4);   // n * 16 bytes in: 8-byte aligned
     b->order.resize(n);
     for (size_t i = 0; i < n; i++) b->order[i] = (int)i;
     std::stable_sort(b->order.begin(), b->order.end(), [&](int a, int c) {
@@ -364,7 +386,9 @@ extern "C" int pngloss_b200_batch_create_ex(pngloss_b200_ctx *ctx, size_t n, con
 extern "C" void pngloss_b200_batch_destroy(pngloss_b200_batch *b) {
     if (!b) return;
     cudaSetDevice(b->ctx->device);
-    cudaStreamSynchronize(b->stream);
+    // an idle batch of the job pool has nothing in flight (its job's last event was waited for): no need to
+    // drain the compute stream it shares with the jobs that are still running
+    if (!b->pooled || b->busy) cudaStreamSynchronize(b->stream);
     for (int k = 0; k < 4; k++)
         if (b->ev[k]) cudaEventDestroy(b->ev[k]);
     if (b->ev_up) cudaEventDestroy(b->ev_up);
@@ -374,6 +398,7 @@ extern "C" void pngloss_b200_batch_destroy(pngloss_b200_batch *b) {
     if (b->hstatus) cudaFreeHost(b->hstatus);
     if (b->hfilters) cudaFreeHost(b->hfilters);
     if (b->scan_slab) cudaFree(b->scan_slab);
+    if (b->own_stream) cudaStreamDestroy(b->stream);
     if (b->hoflags) cudaFreeHost(b->hoflags);
     for (int k = 0; k < 3; k++)
         if (b->ev_scan[k]) cudaEventDestroy(b->ev_scan[k]);
@@ -830,6 +855,7 @@ static int finalize_job(pngloss_b200_job *job) {
             if (st && !first)
                 first = set_err(ctx, st, "image %zu: no acceptable row even at strength 0", i);
         }
+        for (int k = 0; k < 256; k++) ctx->symbols[k] += b->hbhist[k];
         if (job->scanlines) {
             // the colour types are known now: fetch exactly the bytes each image's scanlines take
             for (size_t i = 0; i < job->n && e == cudaSuccess; i++) {
@@ -882,7 +908,7 @@ static int acquire_batch(pngloss_b200_ctx *ctx, const std::vector<uint32_t> &w, 
             }
         }
         pngloss_b200_batch *b = nullptr;
-        int rc = ctx->pool.size() >= 2 ? PNGLOSS_B200_OUT_OF_MEMORY
+        int rc = ctx->pool.size() >= ctx->max_jobs ? PNGLOSS_B200_OUT_OF_MEMORY
                                        : pngloss_b200_batch_create_ex(ctx, w.size(), w.data(), h.data(),
                                                                       PNGLOSS_B200_BATCH_IN_PLACE, &b);
         if (!rc) {
@@ -897,11 +923,23 @@ static int acquire_batch(pngloss_b200_ctx *ctx, const std::vector<uint32_t> &w, 
                 pngloss_b200_batch_destroy(b);
                 return set_err(ctx, PNGLOSS_B200_OUT_OF_MEMORY, "cudaMallocHost(row filters) failed");
             }
+            if (ctx->job_streams) {
+                // pipeline of many small jobs: their kernels run side by side (a job's CTAs take the places another
+                // job's CTAs leave), so every batch computes on a stream of its own
+                cudaStream_t st = nullptr;
+                if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
+                    pngloss_b200_batch_destroy(b);
+                    return set_err(ctx, PNGLOSS_B200_DEVICE_ERROR, "cudaStreamCreate failed");
+                }
+                b->stream = st;
+                b->own_stream = true;
+            }
+            b->pooled = true;
             ctx->pool.push_back(b);
             *out = b;
             return 0;
         }
-        // no room (or two batches already): let the oldest job in flight finish and take its place
+        // no room (or the pipeline is full): let the oldest job in flight finish and take its place
         if (rc != PNGLOSS_B200_OUT_OF_MEMORY || ctx->inflight.empty()) return rc;
         pngloss_b200_job *oldest = nullptr;
         for (pngloss_b200_job *j : ctx->inflight)
@@ -974,6 +1012,9 @@ extern "C" int pngloss_b200_submit(pngloss_b200_ctx *ctx, pngloss_b200_image *im
     }
     if (!rc && e == cudaSuccess)
         e = cudaMemcpyAsync(b->hstatus, b->status, b->n * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                            b->stream);
+    if (!rc && e == cudaSuccess)
+        e = cudaMemcpyAsync(b->hbhist, b->batch_hist, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                             b->stream);
     if (!rc && e == cudaSuccess) e = cudaEventRecord(b->ev_done, b->stream);
     // download stream: pixels (to out_pixels, or back over the input) and row filters

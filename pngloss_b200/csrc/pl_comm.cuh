@@ -143,3 +143,14 @@ extern "C" int pngloss_b200_comm_allreduce_u64(pngloss_b200_ctx *ctx, uint64_t *
     PL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PNGLOSS_B200_SUCCESS;
 }
+
+// Symbol counts (256 x u64) of every image this context's host-buffer calls (pngloss_b200_optimize_batch,
+// pngloss_b200_submit / _wait) have finished so far - the batch-level form of the reference's "used N unique
+// symbols" report (src/pngloss_image.c:315-325).  across_ranks != 0: summed over all ranks of the context's
+// communicator by the NCCL all-reduce (blocking; every rank must call).
+extern "C" int pngloss_b200_ctx_symbol_histogram(pngloss_b200_ctx *ctx, uint64_t out256[256], int across_ranks) {
+    if (!ctx || !out256) return PNGLOSS_B200_INVALID_ARGUMENT;
+    for (int k = 0; k < 256; k++) out256[k] = ctx->symbols[k];
+    if (across_ranks && ctx->comm) return pngloss_b200_comm_allreduce_u64(ctx, out256, 256, 0);
+    return PNGLOSS_B200_SUCCESS;
+}

@@ -13,8 +13,8 @@
 //     4-byte cp.async; the warp that releases a tile last refills it, so nobody ever waits for a free slot;
 //   * tiles are 16 pixels instead of 4: a quarter of the tile overhead;
 //   * the commit of a byte updates the band's own bucket directly (the chosen symbol lies in the band that
-//     was looked up) instead of locating the bucket by division; symbol 0 is a member of both zero buckets,
-//     which removes the extra candidate of the band [-q, 0];
+//     was looked up) instead of locating the bucket by division; symbol 0 - the extra candidate of the band
+//     [-q, 0] - has a table entry of its own ("bucket Z") instead of three table look-ups;
 //   * tables are padded instead of rotated (no index arithmetic against bank conflicts).
 // Requirements (checked by the launcher, pl_api.cu): width % 4 == 0 (16-byte aligned rows for the bulk
 // copies), width < PL_BM_MAX_WIDTH.  Any strength works (outside PL_BM_MIN_STEP..PL_BM_MAX_STEP, and while
@@ -25,8 +25,12 @@
 #pragma once
 #include <stddef.h>
 
-#define PL_L_T 16        // pixels per tile
+#ifndef PL_L_T
+#define PL_L_T 16        // pixels per tile (a multiple of 4)
+#endif
+#ifndef PL_L_STAGES
 #define PL_L_STAGES 2    // tiles in the input ring
+#endif
 #define PL_L_CPW 8       // images per CTA (chains per warp)
 #define PL_L_HALO 4      // pixels of left context in front of a tile (one is used; 16-byte granularity)
 
@@ -61,7 +65,8 @@ struct PlLeanSmem {
     uint32_t delta[PL_L_CPW][PL_FILTERS][PL_L_DELTA_WORDS];
     uint32_t base[PL_L_CPW][PL_L_BASE_WORDS];
     unsigned char rank[PL_L_CPW][PL_FILTERS][PL_L_RANK_BYTES];   // rank of original_frequency[filter][s]
-    uint2 bmk[PL_L_CPW][PL_FILTERS][PL_BM_MAX];         // bucket winners: .x = relative key, .y = base count
+    uint2 bmk[PL_L_CPW][PL_FILTERS][PL_BM_MAX + 1];     // bucket winners: .x = relative key, .y = base count;
+                                                        // entry P1 + N1 ("Z") is symbol 0 alone, at position q
     unsigned dl32[2 * PL_DL32_HALF];                    // Sierra taps by error value (pl_pack_taps6)
     PlLeanOut out[PL_K2_WARPS];
     unsigned long long cost[PL_L_CPW][PL_FILTERS];
@@ -148,11 +153,14 @@ __device__ __forceinline__ unsigned long long pl_lean_row_pass(PlLeanSmem &sm, c
 
     // ---- bucket winners of this candidate at the start of the row (all increments are zero: counts = base) --
     const PlBm bmc = pl_bm_counts(step, W);
+    const int tz = bmc.P1 + bmc.N1;      // bucket Z
     if (live) {
-        for (int t = ch; t < bmc.P1 + bmc.N1; t += 4) {
-            const int lo_t = pl_bm_low(bmc, t, step);
+        for (int t = ch; t < bmc.P1 + bmc.N1 + (bmc.P1 > 0 ? 1 : 0); t += 4) {
+            // negative bucket 0 leaves symbol 0 to bucket 0 and to Z (see pl_bm_counts); Z is symbol 0 alone
+            const int lo_t = t == tz ? -q : pl_bm_low(bmc, t, step);
+            const int p0 = t == tz ? q : 0, p1 = t == bmc.P1 ? q - 1 : q;
             unsigned long long best = 0;
-            for (int p = 0; p <= q; p++) {      // both zero buckets hold symbol 0
+            for (int p = p0; p <= p1; p++) {
                 const unsigned s = (unsigned)(lo_t + p) & 255u;
                 const unsigned long long key =
                     ((unsigned long long)bs[s] << 32) | ((unsigned)rk[s] << PL_KEY_RANK_SHIFT) | (unsigned)(511 - p);
@@ -237,6 +245,17 @@ __device__ __forceinline__ unsigned long long pl_lean_row_pass(PlLeanSmem &sm, c
             // best so far as (count, low word) - the two halves of pl_row_pass's 64-bit candidate key
             unsigned bc = inr ? base_l + (be_x >> PL_BM_COUNT_SHIFT) : 0u;
             unsigned bl = inr ? ((((be_x >> 7) & 255u) << PL_KEY_RANK_SHIFT) | (unsigned)(511 - (wsym - lo))) : 0u;
+            // band [-q, 0]: symbol 0 is not a member of negative bucket 0; its own entry joins in (unless the
+            // clamp cut it off; without a bucket winner inside the band the scan below covers it anyway)
+            if (inr && neg && kq == 0 && hi == 0) {
+                const unsigned long long z64 = *(volatile unsigned long long *)&bmrow[tz];
+                const unsigned zc = (unsigned)(z64 >> 32) + ((unsigned)z64 >> PL_BM_COUNT_SHIFT);
+                const unsigned zl = ((((unsigned)z64 >> 7) & 255u) << PL_KEY_RANK_SHIFT) | (unsigned)(511 + lo);
+                if (zc > bc || (zc == bc && zl > bl)) {
+                    bc = zc;
+                    bl = zl;
+                }
+            }
             const bool need_scan = act && !inr && !(span == 0 && ex == lo);
 #ifdef PL_SIMT_EMU
             if (__any_sync(PL_FULL, need_scan)) PL_EMU_COUNT(PL_CNT_BM_SCAN);
@@ -326,17 +345,18 @@ __device__ __forceinline__ unsigned long long pl_lean_row_pass(PlLeanSmem &sm, c
                     if (tvalid && (unsigned)(sym - lo_u) <= (unsigned)q && s8 > bmc.seam_n && s8 < bmc.seam_p) {
                         // the usual case: the symbol lies in the band that was looked up, i.e. in bucket tl (a band
                         // that the clamp emptied collapses onto a value outside of it), and not in the seam, so
-                        // that sym == s8 and tl is its only bucket
+                        // that sym == s8 and tl is its only bucket - except symbol 0, which lives in bucket 0 and Z
                         PL_EMU_COUNT(PL_CNT_BM_FASTUPD);
-                        if (now >= base_l)
-                            atomicMax(&bmrow[tl].x, ((now - base_l) << PL_BM_COUNT_SHIFT) | rank7 |
-                                                        (unsigned)(127 - (sym - lo_u)));
-                        if (sym == 0) {   // ... and symbol 0 in the zero bucket of the other sign as well
-                            const int t2 = neg ? 0 : bmc.P1;
-                            const unsigned base2 = *(volatile unsigned *)&bmrow[t2].y;
+                        const int tu = sym == 0 ? 0 : tl;
+                        const unsigned base_u = tu == tl ? base_l : *(volatile unsigned *)&bmrow[0].y;
+                        if (now >= base_u)
+                            atomicMax(&bmrow[tu].x, ((now - base_u) << PL_BM_COUNT_SHIFT) | rank7 |
+                                                        (unsigned)(127 - (sym == 0 ? 0 : sym - lo_u)));
+                        if (sym == 0) {
+                            const unsigned base2 = *(volatile unsigned *)&bmrow[tz].y;
                             if (now >= base2)
-                                atomicMax(&bmrow[t2].x, ((now - base2) << PL_BM_COUNT_SHIFT) | rank7 |
-                                                            (unsigned)(127 - (neg ? 0 : q)));
+                                atomicMax(&bmrow[tz].x,
+                                          ((now - base2) << PL_BM_COUNT_SHIFT) | rank7 | (unsigned)(127 - q));
                         }
                     } else {
                         PL_EMU_COUNT(PL_CNT_BM_GENERAL);
@@ -351,10 +371,10 @@ __device__ __forceinline__ unsigned long long pl_lean_row_pass(PlLeanSmem &sm, c
                                                             (unsigned)(127 - (s8 < 0 ? q - rs : rs)));
                         }
                         if (s8 == 0 || s8 >= bmc.seam_p || s8 <= bmc.seam_n) {
-                            // symbol 0: negative bucket 0 (position q); bins >= seam_p: symbol s8 - 256 of the
-                            // last negative bucket; bins <= seam_n: symbol s8 + 256 of the last non-negative one
+                            // symbol 0: its own entry Z (position q); bins >= seam_p: symbol s8 - 256 of the last
+                            // negative bucket; bins <= seam_n: symbol s8 + 256 of the last non-negative one
                             const bool up = s8 <= bmc.seam_n;
-                            const int t2 = s8 == 0 ? bmc.P1 : up ? bmc.P1 - 1 : bmc.P1 + bmc.N1 - 1;
+                            const int t2 = s8 == 0 ? tz : up ? bmc.P1 - 1 : bmc.P1 + bmc.N1 - 1;
                             const int pos2 = s8 == 0 ? q : s8 + (up ? 256 : -256) - pl_bm_low(bmc, t2, step);
                             const unsigned base2 = *(volatile unsigned *)&bmrow[t2].y;
                             if (now >= base2)

@@ -10,6 +10,7 @@
 #include <getopt.h>
 #include <pthread.h>
 #include <stdatomic.h>
+#include <stddef.h>
 #include <stdbool.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -69,74 +70,81 @@ static const struct option long_options[] = {
     {NULL, 0, NULL, 0},
 };
 
-static bool parse_number(const char *arg, unsigned long *out) {
-    char *end;
-    unsigned long v = strtoul(arg, &end, 10);
-    if (end == arg || *end) return false;
-    *out = v;
+/* What an option does when it is seen.  The option letters, long names and messages are the reference's
+ * command line surface (src/pngloss_opts.c:22-47); the parser itself is a table walk. */
+enum action { SET_TRUE, SET_FALSE, TAKE_STRING, TAKE_NUMBER, TAKE_OUTPUT };
+struct option_rule {
+    int id;
+    enum action action;
+    size_t field;              /* offset of the struct options member it touches */
+    const char *number_error;  /* TAKE_NUMBER: message for a non-numeric argument */
+};
+#define FIELD(m) offsetof(struct options, m)
+static const struct option_rule rules[] = {
+    {'v', SET_TRUE, FIELD(verbose), NULL},
+    {'q', SET_FALSE, FIELD(verbose), NULL},
+    {'f', SET_TRUE, FIELD(force), NULL},
+    {arg_no_force, SET_FALSE, FIELD(force), NULL},
+    {arg_skip_larger, SET_TRUE, FIELD(skip_if_larger), NULL},
+    {arg_strip, SET_TRUE, FIELD(strip), NULL},
+    {'h', SET_TRUE, FIELD(print_help), NULL},
+    {'V', SET_TRUE, FIELD(print_version), NULL},
+    {arg_ext, TAKE_STRING, FIELD(extension), NULL},
+    {'o', TAKE_OUTPUT, FIELD(output_file_path), NULL},
+    {'s', TAKE_NUMBER, FIELD(strength), "-s, --strength requires a numeric argument\n"},
+    {'b', TAKE_NUMBER, FIELD(bleed_divider), "-b, --bleed requires a numeric argument\n"},
+    {arg_gpus, TAKE_NUMBER, FIELD(gpus), "--gpus requires a numeric argument\n"},
+    {arg_jobs, TAKE_NUMBER, FIELD(cpu_jobs), "--jobs requires a positive numeric argument\n"},
+};
+
+static bool whole_number(const char *text, unsigned long *value) {
+    if (!*text) return false;
+    char *rest = NULL;
+    const unsigned long v = strtoul(text, &rest, 10);
+    if (*rest) return false;
+    *value = v;
     return true;
 }
 
-/* reference src/pngloss_opts.c:38-136 */
+/* Behaviour of reference src/pngloss_opts.c:38-136: options in any order; "-o -" means stdout; a lone trailing
+ * "-" means stdin (and stdout, unless -o named a file); no arguments at all is "missing arguments". */
 static pngloss_error parse_options(int argc, char *argv[], struct options *o) {
-    int opt;
-    while ((opt = getopt_long(argc, argv, "vqfo:Vhs:b:", long_options, NULL)) != -1) {
-        switch (opt) {
-        case 'v': o->verbose = true; break;
-        case 'q': o->verbose = false; break;
-        case 'f': o->force = true; break;
-        case arg_no_force: o->force = false; break;
-        case arg_ext: o->extension = optarg; break;
-        case 'o':
+    for (int id; (id = getopt_long(argc, argv, "vqfo:Vhs:b:", long_options, NULL)) != -1;) {
+        const struct option_rule *rule = NULL;
+        for (size_t k = 0; k < sizeof rules / sizeof rules[0] && !rule; k++)
+            if (rules[k].id == id) rule = &rules[k];
+        if (!rule) return INVALID_ARGUMENT;            /* getopt already complained */
+        void *member = (char *)o + rule->field;
+        switch (rule->action) {
+        case SET_TRUE: *(bool *)member = true; break;
+        case SET_FALSE: *(bool *)member = false; break;
+        case TAKE_STRING: *(const char **)member = optarg; break;
+        case TAKE_NUMBER:
+            if (!whole_number(optarg, (unsigned long *)member) || (id == arg_jobs && !o->cpu_jobs)) {
+                fputs(rule->number_error, stderr);
+                return INVALID_ARGUMENT;
+            }
+            break;
+        case TAKE_OUTPUT:
             if (o->output_file_path) {
                 fputs("--output option can be used only once\n", stderr);
                 return INVALID_ARGUMENT;
             }
-            if (strcmp(optarg, "-") == 0) o->using_stdout = true;
+            if (optarg[0] == '-' && !optarg[1]) o->using_stdout = true;
             else o->output_file_path = optarg;
             break;
-        case arg_skip_larger: o->skip_if_larger = true; break;
-        case arg_strip: o->strip = true; break;
-        case 'h': o->print_help = true; break;
-        case 'V': o->print_version = true; break;
-        case 's':
-            if (!parse_number(optarg, &o->strength)) {
-                fputs("-s, --strength requires a numeric argument\n", stderr);
-                return INVALID_ARGUMENT;
-            }
-            break;
-        case 'b':
-            if (!parse_number(optarg, &o->bleed_divider)) {
-                fputs("-b, --bleed requires a numeric argument\n", stderr);
-                return INVALID_ARGUMENT;
-            }
-            break;
-        case arg_gpus:
-            if (!parse_number(optarg, &o->gpus)) {
-                fputs("--gpus requires a numeric argument\n", stderr);
-                return INVALID_ARGUMENT;
-            }
-            break;
-        case arg_jobs:
-            if (!parse_number(optarg, &o->cpu_jobs) || !o->cpu_jobs) {
-                fputs("--jobs requires a positive numeric argument\n", stderr);
-                return INVALID_ARGUMENT;
-            }
-            break;
-        default: return INVALID_ARGUMENT;
         }
     }
-    int argn = optind;
-    if (argn < argc) {
-        if (argn == argc - 1 && 0 == strcmp(argv[argn], "-")) {
-            o->using_stdin = true;
-            o->using_stdout = !o->output_file_path;
-            argn = argc - 1;
-        }
-        o->num_files = (unsigned)(argc - argn);
-        o->files = argv + argn;
-    } else if (argn <= 1) {
-        o->missing_arguments = true;
+    const int positional = argc - optind;
+    if (positional <= 0) {
+        o->missing_arguments = optind <= 1;            /* bare "pngloss" */
+        return SUCCESS;
+    }
+    o->files = argv + optind;
+    o->num_files = (unsigned)positional;
+    if (positional == 1 && strcmp(argv[optind], "-") == 0) {
+        o->using_stdin = true;
+        o->using_stdout = o->output_file_path == NULL;
     }
     return SUCCESS;
 }
@@ -147,23 +155,19 @@ static void print_full_version(FILE *fd) {
     fprintf(fd, "   %d CUDA device(s) visible.\n\n", pngloss_b200_device_count());
 }
 
-/* ---- file name helpers (reference src/pngloss.c:305-373) ---------------------------------------------- */
-static bool file_exists(const char *name) {
-    FILE *f = fopen(name, "rb");
-    if (!f) return false;
-    fclose(f);
-    return true;
-}
+/* ---- file name helpers (behaviour of reference src/pngloss.c:305-373) ------------------------------------ */
+static bool file_exists(const char *name) { return access(name, F_OK) == 0; }
 
+/* "x.png" / "x.PNG" -> "x" + newext; any other name gets newext appended */
 static char *add_filename_extension(const char *filename, const char *newext) {
-    size_t x = strlen(filename);
-    char *out = malloc(x + 4 + strlen(newext) + 1);
-    if (!out) return NULL;
-    strcpy(out, filename);
-    if (x > 4 && (strncmp(out + x - 4, ".png", 4) == 0 || strncmp(out + x - 4, ".PNG", 4) == 0))
-        strcpy(out + x - 4, newext);
-    else
-        strcpy(out + x, newext);
+    size_t stem = strlen(filename);
+    if (stem > 4) {
+        const char *suffix = filename + stem - 4;
+        if (!strcmp(suffix, ".png") || !strcmp(suffix, ".PNG")) stem -= 4;
+    }
+    const size_t total = stem + strlen(newext) + 1;
+    char *out = malloc(total);
+    if (out) snprintf(out, total, "%.*s%s", (int)stem, filename, newext);
     return out;
 }
 
@@ -230,8 +234,11 @@ static pngloss_error write_image(png24_image *img, unsigned char *row_filters, c
                                  unsigned scan_bpp, const char *outname, const struct options *o, FILE *log) {
     FILE *out;
     char *tempname = NULL;
+    char *membuf = NULL;      /* stdout: the file is built in memory and only a complete, accepted one is sent - */
+    size_t memlen = 0;        /* a writer that stops at the --skip-if-larger cap must not leave half a PNG there */
     if (o->using_stdout) {
-        out = stdout;
+        out = open_memstream(&membuf, &memlen);
+        if (!out) return OUT_OF_MEMORY_ERROR;
         if (o->verbose) fprintf(log, "  writing compressed image to stdout\n");
     } else {
         tempname = malloc(strlen(outname) + 5);
@@ -251,7 +258,9 @@ static pngloss_error write_image(png24_image *img, unsigned char *row_filters, c
         if (rc == SUCCESS && rename(tempname, outname) != 0) rc = CANT_WRITE_ERROR;
         if (rc) unlink(tempname);
     } else {
-        fflush(out);
+        fclose(out);
+        if (rc == SUCCESS && (fwrite(membuf, 1, memlen, stdout) != memlen || fflush(stdout) != 0)) rc = CANT_WRITE_ERROR;
+        free(membuf);
     }
     free(tempname);
     if (rc && rc != TOO_LARGE_FILE)
@@ -317,7 +326,6 @@ static void flush_logs(struct run *r) {
 static void decode_job(struct run *r, unsigned i) {
     const struct options *o = r->o;
     struct job *j = &r->jobs[i];
-    j->filename = o->using_stdin ? "stdin" : o->files[i];
     j->outname = (char *)o->output_file_path;
     if (!o->using_stdout) {
         if (!j->outname) j->outname = j->outname_free = add_filename_extension(j->filename, o->extension);
@@ -337,6 +345,12 @@ static void decode_job(struct run *r, unsigned i) {
             fprintf(j->logf, "  converted image from gamma %2.1f to gamma 2.2\n", 1.0 / j->input.gamma);
     }
     j->rc = prepare_output_image(&j->input, &j->output);
+    if (!o->using_stdout) {   /* the decoded input is only needed again for the stdout fall-back of --skip-if-larger */
+        free(j->input.rgba_data);
+        free(j->input.row_pointers);
+        j->input.rgba_data = NULL;
+        j->input.row_pointers = NULL;
+    }
     j->row_filters = malloc(j->input.height);   /* NULL is a valid value (reference :262-263) */
     if (!getenv("PNGLOSS_CPU_FILTER"))          /* NULL is a valid value here too: CPU filtering */
         j->scanlines = malloc((size_t)j->input.height * (1 + 4 * (size_t)j->input.width));
@@ -375,6 +389,10 @@ static void encode_job(struct run *r, unsigned i) {
 /* ---- phase 2: the GPU(s).  One host thread and one context per GPU, images assigned longest first ------ */
 struct gpu_shard {
     int device;
+    pngloss_b200_ctx *ctx;             /* created by run_gpus (all contexts share one NCCL communicator) */
+    int reduce;                        /* sum the symbol histogram over the GPUs (NCCL) */
+    uint64_t hist[256];                /* symbol counts of the whole batch (of this GPU's share without NCCL) */
+    int hist_ok;
     pngloss_b200_image *images;
     unsigned *job_index;
     unsigned n;
@@ -387,15 +405,15 @@ struct gpu_shard {
 
 static void *gpu_worker(void *arg) {
     struct gpu_shard *s = arg;
-    pngloss_b200_ctx *ctx = NULL;
-    s->rc = pngloss_b200_ctx_create(&ctx, s->device, NULL);
-    if (s->rc) {
+    pngloss_b200_ctx *ctx = s->ctx;
+    if (!ctx) {
+        s->rc = PNGLOSS_B200_DEVICE_ERROR;
         snprintf(s->err, sizeof s->err, "no usable CUDA device %d (pngloss_b200 has no CPU fallback)", s->device);
         return NULL;
     }
+    if (!s->n) return NULL;
     s->rc = pngloss_b200_optimize_batch(ctx, s->images, s->n, s->strength, s->bleed);
     if (s->rc && s->rc != PNGLOSS_B200_NO_ACCEPTABLE_ROW) snprintf(s->err, sizeof s->err, "%s", pngloss_b200_ctx_error(ctx));
-    pngloss_b200_ctx_destroy(ctx);
     return NULL;
 }
 
@@ -405,17 +423,92 @@ static int by_pixels_desc(const void *a, const void *b) {
     return px < py ? 1 : px > py ? -1 : 0;
 }
 
+/* The GPUs of a run: one context per GPU, created with the first chunk of files and kept until the end; with
+ * several GPUs the contexts share one NCCL communicator. */
+static struct {
+    pngloss_b200_ctx *ctx[64];
+    unsigned n;
+    int nccl, ready;
+    unsigned images;
+} gpus;
+
+static void open_gpus(const struct options *o, unsigned n_images) {
+    if (gpus.ready) return;
+    gpus.ready = 1;
+    int visible = pngloss_b200_device_count();
+    int first_dev = getenv("PNGLOSS_B200_DEVICE") ? atoi(getenv("PNGLOSS_B200_DEVICE")) : 0;
+    unsigned ngpu = o->gpus ? (unsigned)o->gpus : (visible > 0 ? (unsigned)visible : 1);
+    if (visible > 0 && ngpu > (unsigned)visible) ngpu = (unsigned)visible;
+    if (ngpu > n_images) ngpu = n_images;
+    if (ngpu > 64) ngpu = 64;
+    if (!ngpu) ngpu = 1;
+    gpus.n = ngpu;
+    int all = 1;
+    for (unsigned g = 0; g < ngpu; g++) {
+        if (pngloss_b200_ctx_create(&gpus.ctx[g], first_dev + (int)g, NULL)) gpus.ctx[g] = NULL;
+        all &= gpus.ctx[g] != NULL;
+    }
+    if (ngpu > 1 && all) {
+        gpus.nccl = pngloss_b200_comm_init_all(gpus.ctx, (int)ngpu) == 0;
+        if (!gpus.nccl && o->verbose)
+            fprintf(stderr, "  note: no NCCL communicator (%s); symbol counts are added up on the host\n",
+                    pngloss_b200_ctx_error(gpus.ctx[0]));
+    }
+}
+
+/* Batch-level form of the reference's per-image "used N unique symbols" (src/pngloss_image.c:315-325): the
+ * symbol histogram of everything the run quantised, summed over the GPUs by the library's NCCL all-reduce. */
+static void *histogram_worker(void *arg) {
+    struct gpu_shard *s = arg;
+    s->hist_ok = s->ctx && pngloss_b200_ctx_symbol_histogram(s->ctx, s->hist, s->reduce) == 0;
+    return NULL;
+}
+
+static void close_gpus(const struct options *o) {
+    if (!gpus.ready) return;
+    if (o->verbose && gpus.images) {
+        struct gpu_shard *sh = calloc(gpus.n, sizeof *sh);
+        pthread_t *tid = calloc(gpus.n, sizeof *tid);
+        for (unsigned g = 0; sh && tid && g < gpus.n; g++) {
+            sh[g].ctx = gpus.ctx[g];
+            sh[g].reduce = gpus.nccl;
+            if (gpus.n == 1 || pthread_create(&tid[g], NULL, histogram_worker, &sh[g])) {
+                histogram_worker(&sh[g]);
+                tid[g] = 0;
+            }
+        }
+        uint64_t total[256] = {0}, bytes = 0;
+        unsigned unique = 0;
+        int ok = sh && tid;
+        for (unsigned g = 0; ok && g < gpus.n; g++)
+            if (gpus.n > 1 && tid[g]) pthread_join(tid[g], NULL);
+        for (unsigned g = 0; ok && g < (gpus.nccl ? 1u : gpus.n); g++) {
+            ok &= sh[g].hist_ok;
+            for (int k = 0; k < 256; k++) total[k] += sh[g].hist[k];
+        }
+        for (int k = 0; k < 256; k++) {
+            unique += total[k] != 0;
+            bytes += total[k];
+        }
+        if (ok)
+            fprintf(stderr, "batch of %u image%s on %u GPU%s: used %u unique symbols in %llu bytes%s\n", gpus.images,
+                    gpus.images == 1 ? "" : "s", gpus.n, gpus.n == 1 ? "" : "s", unique, (unsigned long long)bytes,
+                    gpus.nccl ? " (histogram summed over the GPUs by NCCL)" : "");
+        free(sh);
+        free(tid);
+    }
+    for (unsigned g = 0; g < gpus.n; g++) pngloss_b200_ctx_destroy(gpus.ctx[g]);
+    gpus.ready = 0;
+}
+
 static void run_gpus(struct run *r) {
     const struct options *o = r->o;
     unsigned n_loaded = 0;
     for (unsigned i = 0; i < r->n; i++) n_loaded += r->jobs[i].loaded;
     if (!n_loaded) return;
-    int visible = pngloss_b200_device_count();
-    int first_dev = getenv("PNGLOSS_B200_DEVICE") ? atoi(getenv("PNGLOSS_B200_DEVICE")) : 0;
-    unsigned ngpu = o->gpus ? (unsigned)o->gpus : (visible > 0 ? (unsigned)visible : 1);
-    if (visible > 0 && ngpu > (unsigned)visible) ngpu = (unsigned)visible;
-    if (ngpu > n_loaded) ngpu = n_loaded;
-    if (!ngpu) ngpu = 1;
+    open_gpus(o, n_loaded);
+    gpus.images += n_loaded;
+    const unsigned ngpu = gpus.n;
 
     /* all loaded images, largest first, each to the GPU with the fewest pixels so far */
     struct tagged { pngloss_b200_image im; unsigned job; } *all = calloc(n_loaded, sizeof *all);
@@ -436,7 +529,8 @@ static void run_gpus(struct run *r) {
     }
     qsort(all, n_loaded, sizeof *all, by_pixels_desc);   /* struct starts with the image: same comparator */
     for (unsigned g = 0; g < ngpu; g++) {
-        shards[g].device = first_dev + (int)g;
+        shards[g].device = (int)g;
+        shards[g].ctx = gpus.ctx[g];
         shards[g].images = calloc(n_loaded, sizeof(pngloss_b200_image));
         shards[g].job_index = calloc(n_loaded, sizeof(unsigned));
         shards[g].strength = (unsigned)o->strength;
@@ -459,7 +553,6 @@ static void run_gpus(struct run *r) {
         }
     for (unsigned g = 0; g < ngpu; g++)
         if (ngpu > 1 && tid[g]) pthread_join(tid[g], NULL);
-
     for (unsigned g = 0; g < ngpu; g++) {
         struct gpu_shard *s = &shards[g];
         if (s->rc && s->err[0]) fprintf(stderr, "  error: %s\n", s->err);
@@ -482,6 +575,33 @@ static void run_gpus(struct run *r) {
     free(tid);
     free(shards);
     free(all);
+}
+
+/* width * height of a PNG from its IHDR (0 if the file cannot be read: it will fail in decode_job with a message) */
+static unsigned long long decoded_bytes_estimate(const char *filename) {
+    unsigned char hdr[24];
+    FILE *f = fopen(filename, "rb");
+    if (!f) return 0;
+    const size_t got = fread(hdr, 1, sizeof hdr, f);
+    fclose(f);
+    if (got != sizeof hdr || memcmp(hdr + 12, "IHDR", 4)) return 0;
+    const unsigned long long w = ((unsigned long long)hdr[16] << 24) | (hdr[17] << 16) | (hdr[18] << 8) | hdr[19];
+    const unsigned long long h = ((unsigned long long)hdr[20] << 24) | (hdr[21] << 16) | (hdr[22] << 8) | hdr[23];
+    return w * h * 13ull + h;
+}
+
+static unsigned long long host_budget_bytes(void) {
+    const char *env = getenv("PNGLOSS_HOST_BUDGET_MB");
+    if (env && atoll(env) > 0) return (unsigned long long)atoll(env) << 20;
+    unsigned long long avail_kb = 0;
+    FILE *f = fopen("/proc/meminfo", "r");
+    if (f) {
+        char line[128];
+        while (fgets(line, sizeof line, f))
+            if (sscanf(line, "MemAvailable: %llu kB", &avail_kb) == 1) break;
+        fclose(f);
+    }
+    return avail_kb ? avail_kb * 1024ull / 2 : 8ull << 30;
 }
 
 int main(int argc, char *argv[]) {
@@ -525,15 +645,43 @@ int main(int argc, char *argv[]) {
 
     struct run r = {&o, calloc(o.num_files, sizeof(struct job)), o.num_files};
     if (!r.jobs) return OUT_OF_MEMORY_ERROR;
-    flush_logs(&r);                    /* opens the per-file message buffers */
+    for (unsigned i = 0; i < r.n; i++) r.jobs[i].filename = o.using_stdin ? "stdin" : o.files[i];
 
-    parallel_for(&r, decode_job);      /* 1. decode every input (CPU threads) */
-    flush_logs(&r);
-    run_gpus(&r);                      /* 2. one batched call per GPU replaces the per-file optimize_with_rows
-                                             (reference src/pngloss.c:266) */
-    flush_logs(&r);
-    parallel_for(&r, encode_job);      /* 3. encode every output (CPU threads) */
-    flush_logs(&r);
+    /* The reference handles one file at a time (src/pngloss.c:173-205); the GPU wants many.  Files are taken in
+     * chunks whose decoded size (input + output pixels + scanlines, about 13 bytes per pixel) fits a host-memory
+     * budget - PNGLOSS_HOST_BUDGET_MB, default half of the available memory - so that a directory of thousands
+     * of large PNGs neither exhausts the host nor starves the GPU: decode chunk, one batched call per GPU, encode,
+     * free, next chunk. */
+    const unsigned long long budget = host_budget_bytes();
+    for (unsigned start = 0; start < r.n;) {
+        unsigned end = start;
+        unsigned long long need = 0;
+        while (end < r.n) {
+            const unsigned long long est = o.using_stdin ? 0 : decoded_bytes_estimate(r.jobs[end].filename);
+            if (end > start && need + est > budget) break;
+            need += est;
+            end++;
+        }
+        struct run chunk = {&o, r.jobs + start, end - start};
+        flush_logs(&chunk);                    /* opens the per-file message buffers */
+        parallel_for(&chunk, decode_job);      /* 1. decode the chunk's inputs (CPU threads) */
+        flush_logs(&chunk);
+        run_gpus(&chunk);                      /* 2. one batched call per GPU replaces the per-file
+                                                     optimize_with_rows (reference src/pngloss.c:266) */
+        flush_logs(&chunk);
+        parallel_for(&chunk, encode_job);      /* 3. encode the chunk's outputs (CPU threads) */
+        flush_logs(&chunk);
+        for (unsigned i = start; i < end; i++) {   /* pixels go now; results and messages stay for the summary */
+            struct job *j = &r.jobs[i];
+            rwpng_free_image24(&j->input);
+            rwpng_free_image24(&j->output);
+            free(j->row_filters);
+            free(j->scanlines);
+            j->row_filters = j->scanlines = NULL;
+        }
+        start = end;
+    }
+    close_gpus(&o);
 
     unsigned error_count = 0, skipped_count = 0;
     pngloss_error latest_error = SUCCESS;
@@ -544,10 +692,6 @@ int main(int argc, char *argv[]) {
             if (j->rc == TOO_LOW_QUALITY || j->rc == TOO_LARGE_FILE) skipped_count++;
             else error_count++;
         }
-        rwpng_free_image24(&j->input);
-        rwpng_free_image24(&j->output);
-        free(j->row_filters);
-        free(j->scanlines);
         free(j->outname_free);
         if (j->logf && j->logf != stderr) fclose(j->logf);
         free(j->log);

@@ -19,10 +19,15 @@
 #ifndef PL_PNG_H
 #define PL_PNG_H
 
+#include <setjmp.h>
 #include <stdbool.h>
 #include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
+
+/* Types below are layout-identical to the reference's src/rwpng.h (same members, order and enum values), so
+ * that the reference's own src/pngloss.c, compiled against ITS rwpng.h, links against this reader / writer
+ * unchanged (oracle/Makefile target refcli; tests/test_gpu_cli.py runs that binary). */
 
 /* reference src/rwpng.h:23-38 */
 typedef enum {
@@ -54,13 +59,20 @@ struct rwpng_chunk {
     unsigned char location;
 };
 
+/* reference src/rwpng.h:52-60; this reader only ever reports NONE, SRGB and GAMA_ONLY (no LCMS / Cocoa) */
 typedef enum {
     RWPNG_NONE,
-    RWPNG_SRGB,      /* sRGB chunk present: written back as gAMA + sRGB */
-    RWPNG_GAMA_ONLY, /* gAMA only (or nothing): no colour chunk is written */
+    RWPNG_SRGB,           /* sRGB chunk present: written back as gAMA + sRGB */
+    RWPNG_ICCP,
+    RWPNG_ICCP_WARN_GRAY,
+    RWPNG_GAMA_CHRM,
+    RWPNG_GAMA_ONLY,      /* gAMA only (or nothing): no colour chunk is written */
+    RWPNG_COCOA,
 } rwpng_color_transform;
 
+/* reference src/rwpng.h:62-75 */
 typedef struct {
+    jmp_buf jmpbuf;       /* libpng's error exit in the reference; unused here, kept for the layout */
     uint32_t width;
     uint32_t height;
     size_t file_size;

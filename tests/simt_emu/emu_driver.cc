@@ -4,6 +4,8 @@
 #include "../../pngloss_b200/csrc/pl_kernels.cuh"
 
 #include <vector>
+unsigned long long pl_t_stats[16];
+extern "C" void emu_tstats(unsigned long long *o){ for(int i=0;i<16;i++){o[i]=pl_t_stats[i]; pl_t_stats[i]=0;} }
 
 template <int LPC>
 static void run_k2(const PlImageDev *imgs, const int *slots, int nblocks, int strength, int bleed,

@@ -148,3 +148,86 @@ def test_cli_gpu_scanlines_give_the_same_files_as_cpu_filtering(tmp_path, oracle
         outs[mode] = {key: open(str(d / f"{key}-loss.png"), "rb").read() for key in imgs}
     for key in imgs:
         assert outs["gpu"][key] == outs["cpu"][key], key
+
+
+# ---- the reference's OWN main(): src/pngloss.c + src/pngloss_opts.c, unmodified, linked with the product --------
+REFMAIN = os.path.join(ROOT, "oracle", "_ref", "pngloss_refmain")
+
+
+def test_reference_main_linked_against_the_product(tmp_path, oracle):
+    """oracle/_ref/pngloss_refmain is the reference's unmodified command line (its main(), its per-file loop,
+    its optimize_with_rows call site src/pngloss.c:266, its option parser) compiled against the reference's
+    own headers and linked with libpngloss_b200.so + the product's PNG reader / writer (oracle/Makefile refcli;
+    built in the dev container, where /root/reference exists, and shipped prebuilt).  What it writes must
+    decode to the oracle's pixels and carry the oracle's filter on every row - the drop-in, proven through the
+    reference's own call site."""
+    if not os.path.exists(REFMAIN):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "refcli"], check=False)
+    if not os.path.exists(REFMAIN):
+        pytest.skip("oracle/_ref/pngloss_refmain not built (needs /root/reference)")
+    imgs = fixture_images(oracle)
+    paths = []
+    for key, rgba in imgs.items():
+        p = str(tmp_path / f"{key}.png")
+        Image.fromarray(rgba, "RGBA").save(p)
+        paths.append(p)
+    r = subprocess.run([REFMAIN, "-v", "-s", "19", "-b", "2", *paths], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for key, rgba in imgs.items():
+        out = str(tmp_path / f"{key}-loss.png")
+        want_px, want_rf = oracle.optimize(rgba, 19, 2, True)
+        got = np.array(Image.open(out).convert("RGBA"))
+        assert np.array_equal(got, want_px), key
+        filt, _ = png_filter_bytes(out)
+        assert filt == [MASK_TO_TYPE[m] for m in want_rf], key
+    # the stdin -> stdout mode the website front end execs (reference website/pnglossapi.go:543-556)
+    rose = [c for c in GOLDEN if c["name"] == "rose"][0]
+    rgba = load_input(rose, oracle)
+    src = str(tmp_path / "rose_in.png")
+    Image.fromarray(rgba, "RGBA").save(src)
+    r = subprocess.run([REFMAIN, "-s30", "-b1", "-"], input=open(src, "rb").read(), capture_output=True)
+    assert r.returncode == 0, r.stderr
+    out = str(tmp_path / "rose_out.png")
+    open(out, "wb").write(r.stdout)
+    want_px, _ = oracle.optimize(rgba, 30, 1, True)
+    assert np.array_equal(np.array(Image.open(out).convert("RGBA")), want_px)
+
+
+def test_cli_stdout_skip_if_larger_sends_one_complete_png(tmp_path, oracle):
+    """stdout + --skip-if-larger with a result that is not smaller: stdout must carry exactly one complete PNG
+    (the original), not the beginning of the rejected file followed by the original."""
+    img = oracle.synth(48, 32, 21)
+    src = str(tmp_path / "in.png")
+    Image.fromarray(img, "RGBA").save(src)
+    first = str(tmp_path / "first.png")
+    assert subprocess.run([CLI, "-s", "0", "-o", first, src]).returncode == 0
+    data = open(first, "rb").read()
+    r = subprocess.run([CLI, "-s", "0", "--skip-if-larger", "-"], input=data, capture_output=True)
+    assert r.returncode == 98, r.stderr
+    assert r.stdout.count(b"\x89PNG\r\n\x1a\n") == 1 and r.stdout.count(b"IEND") == 1
+    out = str(tmp_path / "stdout.png")
+    open(out, "wb").write(r.stdout)
+    assert np.array_equal(np.array(Image.open(out).convert("RGBA")), img)
+
+
+def test_cli_chunks_under_a_small_host_budget(tmp_path, oracle):
+    """PNGLOSS_HOST_BUDGET_MB=1 forces the file list through several decode / GPU / encode chunks; results and
+    the verbose batch summary are those of a single pass."""
+    imgs = {f"s{i}": oracle.synth(160 + 4 * i, 120, 300 + i) for i in range(7)}
+    paths = []
+    for key, rgba in imgs.items():
+        p = str(tmp_path / f"{key}.png")
+        Image.fromarray(rgba, "RGBA").save(p)
+        paths.append(p)
+    env = dict(os.environ, PNGLOSS_HOST_BUDGET_MB="1")
+    r = subprocess.run([CLI, "-v", "-s", "20", "--", *paths], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    assert "Compressed 7 images." in r.stderr
+    assert "batch of 7 images on 1 GPU: used" in r.stderr
+    total = 0
+    for key, rgba in imgs.items():
+        want_px, want_rf, tr = oracle.optimize(rgba, 20, 2, True, trace=True)
+        got = np.array(Image.open(str(tmp_path / f"{key}-loss.png")).convert("RGBA"))
+        assert np.array_equal(got, want_px), key
+        total += int(tr["final_frequency"].sum())
+    assert f"in {total} bytes" in r.stderr

@@ -35,9 +35,11 @@ def run_dropin(img, s, b, want_filters=True):
 
 
 # ---- golden vectors produced by the unmodified reference ------------------------------------------
-@pytest.mark.parametrize("c", cases("small", "medium"), ids=case_id)
+@pytest.mark.parametrize("c", cases("small", "medium", "suite"), ids=case_id)
 def test_golden_through_dropin_entry(oracle, c):
     img = load_input(c, oracle)
+    if img is None:
+        pytest.skip("suite image not available (tests/golden/suite_fixtures.npz)")
     assert sha16(img) == c["in_sha"]
     px, rf = run_dropin(img, c["strength"], c["bleed"], c["filters"])
     assert sha16(px) == c["px_sha"]
@@ -661,3 +663,26 @@ def test_lean_kernel_4k_golden_24_images(ctx, oracle):
     ctx.set_lanes(0)
     ctx.set_bucket_maxima(-1)
     ctx.set_lean(-1)
+
+
+def test_full_8192x8192_golden(ctx, oracle):
+    """BASELINE configs[4]'s image size in full: one 8192 x 8192 synthetic image (seed 1000, strength 20) through
+    the device-resident batch must hash to what the unmodified reference produced (tier "huge" golden, made by
+    tests/golden/make_golden_r2.py; 268 MB in, 268 MB out)."""
+    huge = cases("huge")
+    if not huge:
+        pytest.skip("no 8192 x 8192 golden in golden.json")
+    c = huge[0]
+    src = c["src"]
+    batch = pngloss_b200.Batch(ctx, [src["w"]], [src["h"]], in_place=True)
+    batch.synth(0, src["seed"])
+    batch.run(c["strength"], c["bleed"])
+    st, bpp, _ = batch.finish()
+    assert (st == 0).all() and (bpp == 4).all()
+    out = np.zeros((src["h"], src["w"], 4), np.uint8)
+    rf = np.zeros(src["h"], np.uint8)
+    batch.download(0, out, rf)
+    ctx.sync()
+    batch.close()
+    assert sha16(rf) == c["filt_sha"] and filter_counts(rf) == c["nsuap"]
+    assert sha16(out) == c["px_sha"]

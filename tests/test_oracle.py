@@ -100,3 +100,34 @@ def test_ulog2_identity():
     for f in fs:
         clz32 = 32 - f.bit_length()
         assert ((2**64 - 1) // f).bit_length() == 33 + clz32, f
+
+
+def test_int16_wrap_is_unreachable(oracle):
+    """The error cells are int16 and the reference relies on wrap-on-store (src/color_delta.h:6); the kernels
+    keep that narrowing explicitly.  No input can actually reach it: every error cell is a convex combination of
+    earlier (here - back) differences (the ten Sierra taps of a pixel sum to the difference, a cell's incoming
+    weights sum to 32/32), and |here - back| never exceeds max(|error|, 255 + strength), so cells stay within
+    about +-511.  Adversarial inputs at the extreme settings confirm it: zero wraps, and the restatement still
+    equals the reference."""
+    import ctypes
+    from checkers import Reference, have_reference
+    oracle.lib.oracle_int16_wraps.restype = ctypes.c_uint64
+    oracle.lib.oracle_int16_wraps.argtypes = [ctypes.c_int]
+    rng = np.random.default_rng(1)
+    h, w = 6, 400
+    checker = np.zeros((h, w, 4), np.uint8)
+    checker[(np.add.outer(np.arange(h), np.arange(w)) % 2) == 0] = 255
+    checker[..., 3] = np.where(checker[..., 0] > 0, 255, 1)
+    stripes = np.full((h, w, 4), 255, np.uint8)
+    stripes[:, ::7] = 0
+    stripes[..., 3] = 200
+    noise = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    ref = Reference() if have_reference() else None
+    for img in (checker, stripes, noise):
+        for (s, b) in ((255, 1), (200, 1), (85, 1)):
+            oracle.lib.oracle_int16_wraps(1)
+            px, rf = oracle.optimize(img, s, b, True)
+            assert oracle.lib.oracle_int16_wraps(1) == 0
+            if ref is not None:
+                px2, rf2 = ref.optimize(img, s, b, True)
+                assert np.array_equal(px, px2) and np.array_equal(rf, rf2)
