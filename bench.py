@@ -569,12 +569,13 @@ def e2e_job_api(a, ctx, pngloss_b200, seeds, n, w, h, world, allmax, allmin_int)
     consumer such as the PNG encoder would have taken them before the segment comes round again).  Every step
     uploads and downloads every image; the byte counts below are what crosses PCIe."""
     img_bytes = w * h * 4
-    pipeline = a.config == "3s" and n >= 1184
+    pipeline = a.config == "3s" and n * img_bytes * 2 > 150e9     # two whole steps do not fit the device
     if pipeline:
         per_job = 296
         jobs_per_step = -(-n // per_job)
         in_flight = min(jobs_per_step, 12) + 3
         ctx.set_lanes(1)
+        ctx.set_lean(1)                         # every job is a small grid; together they fill three CTAs per SM
         ctx.set_pipeline(in_flight)
         out_segments = 4
     else:

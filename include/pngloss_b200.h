@@ -81,9 +81,10 @@ int pngloss_b200_ctx_set_lanes(pngloss_b200_ctx *ctx, int lanes_per_channel);
  * fall-back, 0 = scan every band, -1 = choose from the strength (default).  A tuning knob, results
  * never depend on it. */
 int pngloss_b200_ctx_set_bucket_maxima(pngloss_b200_ctx *ctx, int mode);
-/* Kernel variant for batches that run one lane per channel with the winner table: 1 / -1 (default) = the lean
- * kernel (bulk-copy tile ring, three CTAs per SM) where its conditions hold (every width a multiple of 4),
- * 0 = always the generic kernel.  A tuning knob, results never depend on it. */
+/* Kernel variant for batches that run one lane per channel with the winner table: 1 = the lean kernel (bulk-copy
+ * tile ring, three CTAs per SM) wherever its conditions hold (every width a multiple of 4), -1 (default) = the
+ * same, but only for grids of more than two CTAs per SM (where it is the faster one), 0 = always the generic
+ * kernel.  A tuning knob, results never depend on it. */
 int pngloss_b200_ctx_set_lean(pngloss_b200_ctx *ctx, int mode);
 /* CUDA-event stopwatch on the context's stream (what bench.py times with). */
 int pngloss_b200_ctx_timer_start(pngloss_b200_ctx *ctx);

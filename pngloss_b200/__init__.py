@@ -248,7 +248,7 @@ class Context:
         self._check(self.lib.pngloss_b200_ctx_set_bucket_maxima(self.handle, mode))
 
     def set_lean(self, mode: int):
-        """1 / -1: the lean kernel where it applies (default), 0: always the generic kernel"""
+        """1: the lean kernel wherever it applies, -1 (default): only for grids beyond two CTAs per SM, 0: never"""
         self._check(self.lib.pngloss_b200_ctx_set_lean(self.handle, mode))
 
     # ---- multi-GPU: the library's own NCCL communicator (pl_comm.cuh) --------------------------------------

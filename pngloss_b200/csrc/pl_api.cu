@@ -590,7 +590,10 @@ static int launch_run(pngloss_b200_batch *b, unsigned strength, long bleed, int 
     // the lean kernel needs 16-byte aligned rows for its bulk copies
     bool w4 = true;
     for (size_t i = 0; i < b->n; i++) w4 = w4 && (b->w[i] & 3u) == 0;
-    const bool lean = lpc == 1 && bm && w4 && wmax < PL_BM_MAX_WIDTH && ctx->lean != 0;
+    // ... and it only wins where its third CTA per SM is used (measured, profiles/r2_sweep_lean.txt: 3164 against
+    // 2551 Mpx/s at 444 CTAs, 2407 against 2978 at 296): by default only for grids beyond two CTAs per SM
+    const bool lean = lpc == 1 && bm && w4 && wmax < PL_BM_MAX_WIDTH &&
+                      (ctx->lean > 0 || (ctx->lean < 0 && nblocks > 2 * 148));
     int rc;
     if (lean) rc = launch_k2_lean(b, nblocks, strength, bleed);
     else

@@ -1441,18 +1441,22 @@ __global__ void __launch_bounds__(256) pl_k_synth(uchar4 *dst, uint32_t w, uint3
     const unsigned long long n = (unsigned long long)w * h;
     const unsigned dx = w > 1 ? w - 1 : 1, dy = h > 1 ? h - 1 : 1;
     const unsigned dxy = (w + h > 2) ? w + h - 2 : 1;
+    // images are at most 2^29 pixels (batch_create), so x, y, x + y times 255 fit 32 bits
     for (unsigned long long p = (unsigned long long)blockIdx.x * 256 + threadIdx.x; p < n;
          p += (unsigned long long)gridDim.x * 256) {
-        const unsigned x = (unsigned)(p % w), y = (unsigned)(p / w);
+        const unsigned p32 = (unsigned)p, y = p32 / w, x = p32 - y * w;
         int base[4];
-        base[0] = (int)((unsigned long long)x * 255 / dx);
-        base[1] = (int)((unsigned long long)y * 255 / dy);
-        base[2] = (int)(((unsigned long long)x + y) * 255 / dxy);
+        base[0] = (int)(x * 255u / dx);
+        base[1] = (int)(y * 255u / dy);
+        base[2] = (int)((x + y) * 255u / dxy);
         base[3] = 255 - base[0] / 2;
         unsigned char v[4];
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            const int nz = (int)(pl_splitmix64((seed << 40) + p * 4 + c) % 17) - 8;
+            // z mod 17 for a 64-bit z: 2^32 = 1 (mod 17), so it is (high word + low word) mod 17
+            const unsigned long long z = pl_splitmix64((seed << 40) + p * 4 + c);
+            const unsigned fold = (unsigned)(z >> 32) % 17u + (unsigned)z % 17u;
+            const int nz = (int)(fold % 17u) - 8;
             int t = base[c] + nz;
             t = t < 0 ? 0 : t > 255 ? 255 : t;
             if (c == 3 && (y / 64) % 4 == 0 && x < w / 16) t = 0;
