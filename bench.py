@@ -58,8 +58,10 @@ def parse_args():
     ap.add_argument("--config", default="3s", choices=["1", "2", "3", "3s", "4", "5"],
                     help="BASELINE.json config (see the module docstring); default 3s = the metric's config, saturated")
     ap.add_argument("--images", type=int, default=0,
-                    help="3s: images per GPU per step (default 3552 = 24 per SM, three CTAs of 8 images); "
-                         "4 / 5: total images of the job (default 1024 / 64)")
+                    help="3s: images per GPU per step (default 2368 = 16 per SM: two whole steps fit the device, so the "
+                         "end-to-end pipeline overlaps copies and kernels step against step; 3552 = 24 per SM "
+                         "runs the large-batch kernel, see DESIGN.md); 4 / 5: total images of the job "
+                         "(default 1024 / 64)")
     ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--strength", type=int, default=-1)
@@ -73,7 +75,7 @@ def parse_args():
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows per core of the CPU sample (0 = auto)")
     a = ap.parse_args()
     spec = {
-        "3s": dict(w=3840, h=2160, strength=20, per_gpu=3552, total=0, scaling="weak", source="synth", seed0=4),
+        "3s": dict(w=3840, h=2160, strength=20, per_gpu=2368, total=0, scaling="weak", source="synth", seed0=4),
         "1": dict(w=180, h=215, strength=19, per_gpu=1, total=0, scaling="weak", source="david", seed0=0),
         "2": dict(w=512, h=512, strength=20, per_gpu=1, total=0, scaling="weak", source="lena", seed0=0),
         "3": dict(w=3840, h=2160, strength=20, per_gpu=1, total=0, scaling="weak", source="synth", seed0=4),
@@ -341,7 +343,7 @@ def main():
     # the step then re-creates its inputs on the device first (the synthetic generator kernel, ~0.5 % of the
     # step, inside the timed region and counted in gpu_launches).  Small batches keep inputs and outputs apart.
     img_bytes = w * h * 4
-    in_place = a.source == "synth" and n * img_bytes * 2 > 150e9
+    in_place = a.source == "synth" and n * img_bytes * 2 > 165e9
     while True:
         try:
             batch = pngloss_b200.Batch(ctx, [w] * n, [h] * n, in_place=in_place)
@@ -558,18 +560,18 @@ def e2e_single_image(a, ctx, pngloss_b200, host_img, seeds, w, h):
 def e2e_job_api(a, ctx, pngloss_b200, seeds, n, w, h, world, allmax, allmin_int):
     """The step through pngloss_b200_submit / _wait with host buffers.
 
-    Saturated config (3s): a step's images do not fit the device twice, so the step is cut into jobs of 296
-    images (37 CTAs of the large-batch kernel) and the context runs as a pipeline (pngloss_b200_ctx_set_pipeline):
-    every job computes on its own stream, about twelve jobs share the SMs at any time (24 images per SM), and as
-    one job's CTAs finish the next job's take their places while its results go back over PCIe and the job
-    after it is uploaded.  Other configs: one or two jobs per step, two in flight.
+    A job is a whole step and two steps are in flight: the upload of step k+1 and the download of step k-1 run
+    under the kernels of step k.  When two steps do not fit the device (--images 3552: 118 GB each), the step is
+    cut into jobs of 296 images (37 CTAs of the large-batch kernel) and the context runs as a pipeline
+    (pngloss_b200_ctx_set_pipeline): every job computes on its own stream, about twelve jobs share the SMs at any
+    time, and as one job's CTAs finish the next job's take their places.
 
-    Host buffers are rings whose size does not depend on the number of ranks: image i is uploaded from input
-    slot i % slots_in (inputs are never modified) and job j's results land in output ring segment j % 4 (a
-    consumer such as the PNG encoder would have taken them before the segment comes round again).  Every step
-    uploads and downloads every image; the byte counts below are what crosses PCIe."""
+    Host buffers: the output buffer holds a whole job (the pipeline: a ring of four jobs); the input buffer is a
+    ring of at most 20 GB that shrinks to what the host can spare per rank, so that images_per_gpu stays the same
+    at every N: image i is uploaded from input slot i % slots_in (inputs are never modified).  Every step uploads
+    and downloads every image; the byte counts below are what crosses PCIe."""
     img_bytes = w * h * 4
-    pipeline = a.config == "3s" and n * img_bytes * 2 > 150e9     # two whole steps do not fit the device
+    pipeline = a.config == "3s" and n * img_bytes * 2 > 165e9     # two whole steps do not fit the device
     if pipeline:
         per_job = 296
         jobs_per_step = -(-n // per_job)
@@ -579,11 +581,18 @@ def e2e_job_api(a, ctx, pngloss_b200, seeds, n, w, h, world, allmax, allmin_int)
         ctx.set_pipeline(in_flight)
         out_segments = 4
     else:
-        per_job = n if n * img_bytes <= 60e9 else -(-n // 2)
-        jobs_per_step = -(-n // per_job)
+        per_job = n                             # a job is a whole step; two steps in flight
+        jobs_per_step = 1
         in_flight = 2
-        out_segments = 2
-    slots_in = allmin_int(min(n, max(per_job, int(20e9 // img_bytes))))
+        out_segments = 1                        # step k+1's download starts long after step k's wait returned
+    # host rings: the output ring holds whole jobs; the input ring shrinks to what the host can spare (inputs are
+    # never modified, image i is uploaded from slot i % slots_in), at most 20 GB
+    try:
+        avail = int([ln for ln in open("/proc/meminfo") if ln.startswith("MemAvailable")][0].split()[1]) * 1024
+    except Exception:
+        avail = 64 << 30
+    spare = int(0.7 * avail / world) - out_segments * per_job * img_bytes
+    slots_in = allmin_int(max(8, min(n, int(20e9 // img_bytes), spare // img_bytes)))
     src = ctx.pinned_empty((slots_in, h, w, 4))
     dst = ctx.pinned_empty((out_segments * per_job, h, w, 4))
     gen = min(slots_in, 64)
@@ -633,7 +642,8 @@ def e2e_job_api(a, ctx, pngloss_b200, seeds, n, w, h, world, allmax, allmin_int)
            "host_input_ring_images": slots_in, "host_output_ring_images": out_segments * per_job,
            "api": ("pngloss_b200_submit / pngloss_b200_wait, pipeline of %d jobs in flight on their own streams "
                    "(pngloss_b200_ctx_set_pipeline)" % in_flight) if pipeline else
-                  "pngloss_b200_submit / pngloss_b200_wait, two jobs in flight",
+                  "pngloss_b200_submit / pngloss_b200_wait, two steps in flight (the copies of one step run under "
+                  "the kernels of the other)",
            "note": "pinned host rings; every step uploads all its inputs and downloads all its results; the timed "
                    "region starts and ends with an idle device (pipeline fill and drain included)"}
     ctx.free_pinned(src)

@@ -24,6 +24,7 @@ struct pngloss_b200_ctx {
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     int lpc = 0;
     int bm = -1;   // bucket-maxima variant of K2: -1 choose from the strength, 0 off, 1 on
+    int sm_count = 0;
     int lean = -1; // lean kernel (pl_k2_lean) where it applies: -1 yes (default), 0 never, 1 yes
     char err[512] = {0};
     // job API (pngloss_b200_submit / _wait): copy streams, the device batches it recycles, jobs in flight
@@ -128,6 +129,7 @@ extern "C" int pngloss_b200_ctx_create(pngloss_b200_ctx **out, int device, void 
     if (!ctx) return PNGLOSS_B200_OUT_OF_MEMORY;
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return PNGLOSS_B200_DEVICE_ERROR; }
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (cuda_stream) {
         ctx->stream = (cudaStream_t)cuda_stream;
     } else {
@@ -506,16 +508,15 @@ static int launch_k2(pngloss_b200_batch *b, int nblocks, unsigned strength, long
               : launch_k2<LPC, false>(b, nblocks, strength, bleed);
 }
 
-// Lane mapping by batch size, from the B200 sweeps in profiles/ (3840-wide images): with few images
-// only wide lane groups keep the SMs busy (one image per CTA); with more images per SM, packing 4 or 8
-// images per CTA issues ~3x fewer instructions per pixel (1184 images: 1.41 Gpx/s at 8 per CTA, 1.27 at
-// 4, 0.86 at 2, 0.55 at 1).
+// Lane mapping by batch size, from the B200 sweeps in profiles/ (r1_sweep_lanes_bm.txt, r2_sweep_lean.txt).  A
+// chain's step costs 0.51 / 0.58 / 0.65 / 0.67 us with 8 / 4 / 2 / 1 lanes per channel when a CTA has an SM to
+// itself, and 1.3x / 1.7x / 2.1x that with 2 / 3 / 4 CTAs per SM - so: the widest lane groups (fewest images per
+// CTA) that still give every CTA its own SM, and 8 images per CTA once even that needs more CTAs than SMs.
 static int choose_lpc(const pngloss_b200_batch *b) {
     if (b->ctx->lpc) return b->ctx->lpc;
-    if (b->n >= 1184) return 1;
-    if (b->n >= 592) return 2;
-    if (b->n >= 296) return 4;
-    return 8;
+    const size_t sms = b->ctx->sm_count > 0 ? (size_t)b->ctx->sm_count : 148;
+    const size_t per_cta = (b->n + sms - 1) / sms;   // images a CTA must take for one CTA per SM
+    return per_cta <= 1 ? 8 : per_cta <= 2 ? 4 : per_cta <= 4 ? 2 : 1;
 }
 
 // Host-side part of a run: CTA packing, descriptors and the cleared accumulators, enqueued on `stream`
@@ -593,7 +594,7 @@ static int launch_run(pngloss_b200_batch *b, unsigned strength, long bleed, int 
     // ... and it only wins where its third CTA per SM is used (measured, profiles/r2_sweep_lean.txt: 3164 against
     // 2551 Mpx/s at 444 CTAs, 2407 against 2978 at 296): by default only for grids beyond two CTAs per SM
     const bool lean = lpc == 1 && bm && w4 && wmax < PL_BM_MAX_WIDTH &&
-                      (ctx->lean > 0 || (ctx->lean < 0 && nblocks > 2 * 148));
+                      (ctx->lean > 0 || (ctx->lean < 0 && nblocks > 2 * (ctx->sm_count > 0 ? ctx->sm_count : 148)));
     int rc;
     if (lean) rc = launch_k2_lean(b, nblocks, strength, bleed);
     else
