@@ -171,6 +171,10 @@ int pngloss_b200_batch_finish(pngloss_b200_batch *b, int *status, uint32_t *byte
 /* Per-image final symbol histogram [256] and the batch sum [256] (valid after finish). */
 int pngloss_b200_batch_image_histogram(pngloss_b200_batch *b, size_t i, uint32_t *out256);
 int pngloss_b200_batch_histogram(pngloss_b200_batch *b, uint64_t *out256);
+/* The histogram kernel's output for one image (valid after finish): counts of (byte - predictor) over the
+ * original image per filter and RGBA channel, [5][4][256]; summed over the channels of the image's colour mode
+ * it is the reference's original_frequency table (src/optimize_state.c:66-83). */
+int pngloss_b200_batch_image_original_histogram(pngloss_b200_batch *b, size_t i, uint32_t *out5x4x256);
 /* Device address of the batch sum (uint64[256]) for the caller's NCCL all-reduce. */
 void *pngloss_b200_batch_histogram_device(pngloss_b200_batch *b);
 /* Durations of the last run in milliseconds: [0] histogram kernel, [1] quantise kernel,

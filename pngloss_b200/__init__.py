@@ -36,7 +36,8 @@ EXPORTS = [
     "pngloss_b200_batch_upload_rows", "pngloss_b200_batch_synth", "pngloss_b200_batch_run",
     "pngloss_b200_batch_download", "pngloss_b200_batch_download_rows",
     "pngloss_b200_batch_download_input", "pngloss_b200_batch_finish",
-    "pngloss_b200_batch_image_histogram", "pngloss_b200_batch_histogram",
+    "pngloss_b200_batch_image_histogram", "pngloss_b200_batch_image_original_histogram",
+    "pngloss_b200_batch_histogram",
     "pngloss_b200_batch_histogram_device", "pngloss_b200_batch_timings",
     "pngloss_b200_batch_launch_info", "pngloss_b200_batch_scanlines", "pngloss_b200_batch_scanline_info",
     "pngloss_b200_batch_download_scanlines",
@@ -148,6 +149,7 @@ def load_library() -> ctypes.CDLL:
     L.pngloss_b200_batch_download_input.argtypes = [vp, sz, vp, sz]
     L.pngloss_b200_batch_finish.argtypes = [vp, vp, vp, vp]
     L.pngloss_b200_batch_image_histogram.argtypes = [vp, sz, vp]
+    L.pngloss_b200_batch_image_original_histogram.argtypes = [vp, sz, vp]
     L.pngloss_b200_batch_histogram.argtypes = [vp, vp]
     L.pngloss_b200_batch_histogram_device.argtypes = [vp]
     L.pngloss_b200_batch_histogram_device.restype = vp
@@ -442,6 +444,12 @@ class Batch:
     def image_histogram(self, i) -> np.ndarray:
         out = np.zeros(256, np.uint32)
         self.ctx._check(self.lib.pngloss_b200_batch_image_histogram(self.handle, i, out.ctypes.data))
+        return out
+
+    def original_histogram(self, i) -> np.ndarray:
+        """K1's output for image i: counts of (byte - predictor) per filter and RGBA channel, (5, 4, 256)."""
+        out = np.zeros((5, 4, 256), np.uint32)
+        self.ctx._check(self.lib.pngloss_b200_batch_image_original_histogram(self.handle, i, out.ctypes.data))
         return out
 
     def histogram(self) -> np.ndarray:

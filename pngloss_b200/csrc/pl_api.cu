@@ -702,6 +702,18 @@ extern "C" int pngloss_b200_batch_image_histogram(pngloss_b200_batch *b, size_t 
     return PNGLOSS_B200_SUCCESS;
 }
 
+// K1's output for one image: original_frequency per (filter, RGBA channel), 5 x 4 x 256 counts.  Summed over the
+// channels the image's colour mode uses it is the reference's optimize_state_init table (src/optimize_state.c:66-83).
+extern "C" int pngloss_b200_batch_image_original_histogram(pngloss_b200_batch *b, size_t i, uint32_t *out5x4x256) {
+    if (!b || i >= b->n || !out5x4x256) return PNGLOSS_B200_INVALID_ARGUMENT;
+    pngloss_b200_ctx *ctx = b->ctx;
+    PL_CUDA(ctx, cudaSetDevice(ctx->device));
+    PL_CUDA(ctx, cudaMemcpyAsync(out5x4x256, b->himgs[i].chan_hist, PL_FILTERS * 4 * 256 * sizeof(uint32_t),
+                                 cudaMemcpyDeviceToHost, b->stream));
+    PL_CUDA(ctx, cudaStreamSynchronize(b->stream));
+    return PNGLOSS_B200_SUCCESS;
+}
+
 extern "C" int pngloss_b200_batch_histogram(pngloss_b200_batch *b, uint64_t *out256) {
     if (!b || !out256) return PNGLOSS_B200_INVALID_ARGUMENT;
     pngloss_b200_ctx *ctx = b->ctx;

@@ -114,6 +114,32 @@ class Reference:
                                                   ctypes.c_long]
         self.lib.optimize_with_stride.restype = None
 
+    def original_frequency(self, packed: np.ndarray, bpp: int) -> np.ndarray:
+        """original_frequency[5][256] as the reference's own optimize_state_init builds it
+        (src/optimize_state.c:28-86) over a packed bytes_per_pixel image of shape (h, w * bpp)."""
+        class RefImage(ctypes.Structure):          # reference src/pngloss_image.h:7-11
+            _fields_ = [("rows", ctypes.POINTER(ctypes.c_void_p)), ("width", ctypes.c_uint32),
+                        ("height", ctypes.c_uint32), ("bytes_per_pixel", ctypes.c_uint8)]
+
+        class RefState(ctypes.Structure):          # reference src/optimize_state.h:9-16
+            _fields_ = [("x", ctypes.c_uint32), ("y", ctypes.c_uint32), ("pixels", ctypes.c_void_p),
+                        ("color_error", ctypes.c_void_p), ("symbol_frequency", ctypes.c_void_p),
+                        ("symbol_count", ctypes.c_uint64),
+                        ("original_frequency", ctypes.POINTER(ctypes.c_uint32) * 5)]
+        p = np.ascontiguousarray(packed)
+        h, wb = p.shape
+        rows = (ctypes.c_void_p * h)(*[p.ctypes.data + y * wb for y in range(h)])
+        img = RefImage(rows, wb // bpp, h, bpp)
+        st = RefState()
+        self.lib.optimize_state_init.argtypes = [ctypes.POINTER(RefState), ctypes.POINTER(RefImage)]
+        self.lib.optimize_state_init.restype = ctypes.c_int
+        self.lib.optimize_state_destroy.argtypes = [ctypes.POINTER(RefState)]
+        self.lib.optimize_state_destroy.restype = None
+        assert self.lib.optimize_state_init(ctypes.byref(st), ctypes.byref(img)) == 0
+        out = np.stack([np.ctypeslib.as_array(st.original_frequency[f], shape=(256,)).copy() for f in range(5)])
+        self.lib.optimize_state_destroy(ctypes.byref(st))
+        return out
+
     def optimize(self, rgba, strength, bleed, want_filters=True):
         a = np.ascontiguousarray(rgba).copy()
         h, w, _ = a.shape

@@ -231,3 +231,26 @@ def test_cli_chunks_under_a_small_host_budget(tmp_path, oracle):
         assert np.array_equal(got, want_px), key
         total += int(tr["final_frequency"].sum())
     assert f"in {total} bytes" in r.stderr
+
+
+@pytest.mark.skipif(__import__("pngloss_b200").device_count() < 2, reason="needs two GPUs")
+def test_cli_two_gpus_reduce_the_batch_histogram_with_nccl(tmp_path, oracle):
+    """--gpus 2: files sharded over two GPUs (one host thread and context each), results identical to the oracle,
+    and the verbose batch line reports the symbol histogram summed over the GPUs by the library's NCCL call."""
+    imgs = {f"g{i}": oracle.synth(96 + 8 * i, 64, 700 + i) for i in range(6)}
+    paths = []
+    for key, rgba in imgs.items():
+        p = str(tmp_path / f"{key}.png")
+        Image.fromarray(rgba, "RGBA").save(p)
+        paths.append(p)
+    r = subprocess.run([CLI, "-v", "-s", "20", "--gpus", "2", "--", *paths], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "batch of 6 images on 2 GPUs: used" in r.stderr
+    assert "summed over the GPUs by NCCL" in r.stderr, r.stderr
+    total = 0
+    for key, rgba in imgs.items():
+        want_px, want_rf, tr = oracle.optimize(rgba, 20, 2, True, trace=True)
+        got = np.array(Image.open(str(tmp_path / f"{key}-loss.png")).convert("RGBA"))
+        assert np.array_equal(got, want_px), key
+        total += int(tr["final_frequency"].sum())
+    assert f"in {total} bytes" in r.stderr

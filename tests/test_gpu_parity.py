@@ -686,3 +686,25 @@ def test_full_8192x8192_golden(ctx, oracle):
     batch.close()
     assert sha16(rf) == c["filt_sha"] and filter_counts(rf) == c["nsuap"]
     assert sha16(out) == c["px_sha"]
+
+
+def test_k1_original_histogram_against_the_reference(ctx, oracle):
+    """The histogram kernel K1 on the device against the reference's own optimize_state_init
+    (src/optimize_state.c:66-83, called in oracle/_ref; the restatement where that library is absent): per filter,
+    K1's per-channel counts summed over the channels of the colour mode are original_frequency[5][256]."""
+    from checkers import Reference, have_reference
+    ref = Reference() if have_reference() else None
+    for bpp in (1, 2, 3, 4):
+        img = to_bpp(oracle.synth(203, 57, 80 + bpp), bpp)
+        batch = pngloss_b200.Batch(ctx, [203], [57])
+        batch.upload(0, img)
+        batch.run(20, 2)
+        st, got_bpp, _ = batch.finish()
+        assert st[0] == 0 and got_bpp[0] == bpp
+        chan = batch.original_histogram(0)
+        batch.close()
+        chans = {1: [1], 2: [1, 3], 3: [0, 1, 2], 4: [0, 1, 2, 3]}[bpp]
+        folded = chan[:, chans, :].sum(axis=1)
+        packed = np.ascontiguousarray(img[:, :, chans]).reshape(img.shape[0], -1)
+        want = ref.original_frequency(packed, bpp) if ref else oracle.original_frequency(packed, bpp)
+        assert np.array_equal(folded, want), bpp

@@ -131,3 +131,18 @@ def test_int16_wrap_is_unreachable(oracle):
             if ref is not None:
                 px2, rf2 = ref.optimize(img, s, b, True)
                 assert np.array_equal(px, px2) and np.array_equal(rf, rf2)
+
+
+def test_original_frequency_equals_the_reference_init(oracle):
+    """optimize_state_init's original_frequency[5][256] (reference src/optimize_state.c:66-83), called in the
+    reference library itself, against the restatement - for every bytes-per-pixel mode.  (The emulator and GPU
+    tests compare the histogram kernel K1 with the restatement / with this.)"""
+    from checkers import Reference, have_reference, to_bpp
+    if not have_reference():
+        pytest.skip("oracle/_ref not built")
+    ref = Reference()
+    for bpp in (1, 2, 3, 4):
+        img = to_bpp(oracle.synth(37, 13, 70 + bpp), bpp)
+        chans = {1: [1], 2: [1, 3], 3: [0, 1, 2], 4: [0, 1, 2, 3]}[bpp]
+        packed = np.ascontiguousarray(img[:, :, chans]).reshape(img.shape[0], -1)
+        assert np.array_equal(ref.original_frequency(packed, bpp), oracle.original_frequency(packed, bpp)), bpp
