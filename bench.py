@@ -591,7 +591,7 @@ def e2e_job_api(a, ctx, pngloss_b200, seeds, n, w, h, world, allmax, allmin_int)
         avail = int([ln for ln in open("/proc/meminfo") if ln.startswith("MemAvailable")][0].split()[1]) * 1024
     except Exception:
         avail = 64 << 30
-    spare = int(0.7 * avail / world) - out_segments * per_job * img_bytes
+    spare = int(0.6 * avail / world) - out_segments * per_job * img_bytes
     slots_in = allmin_int(max(8, min(n, int(20e9 // img_bytes), spare // img_bytes)))
     src = ctx.pinned_empty((slots_in, h, w, 4))
     dst = ctx.pinned_empty((out_segments * per_job, h, w, 4))
@@ -614,18 +614,37 @@ def e2e_job_api(a, ctx, pngloss_b200, seeds, n, w, h, world, allmax, allmin_int)
         return ([src[i % slots_in] for i in idx], [filters[seg + k] for k in range(len(idx))],
                 [dst[seg + k] for k in range(len(idx))])
 
+    trace = os.environ.get("PNGLOSS_BENCH_TRACE")
+    rank = int(os.environ.get("RANK", "0"))
+
     def run_steps(count):
-        inflight = []
+        # PNGLOSS_BENCH_TRACE=1: host-side time line of every job (seconds since the start of the call): when submit
+        # was entered and returned, when wait was entered and returned.  A wait that returns long after the
+        # kernels' share of the step is what PCIe / host-memory contention looks like.
+        inflight, t0 = [], time.perf_counter()
+
+        def finish(item):
+            job, k, ts0, ts1 = item
+            tw0 = time.perf_counter()
+            res = job.wait()
+            tw1 = time.perf_counter()
+            assert all(r["status"] == 0 for r in res)
+            if trace:
+                print(f"[e2e-trace] rank {rank} job {k} submit {ts0 - t0:.3f}-{ts1 - t0:.3f} "
+                      f"wait {tw0 - t0:.3f}-{tw1 - t0:.3f}", file=sys.stderr, flush=True)
+
+        k = 0
         for _ in range(count):
             for j in range(jobs_per_step):
                 ins, rfs, outs = job_args(j)
-                inflight.append(ctx.submit(ins, rfs, a.strength, a.bleed, outputs=outs))
+                ts0 = time.perf_counter()
+                job = ctx.submit(ins, rfs, a.strength, a.bleed, outputs=outs)
+                inflight.append((job, k, ts0, time.perf_counter()))
+                k += 1
                 if len(inflight) >= in_flight:
-                    res = inflight.pop(0).wait()
-                    assert all(r["status"] == 0 for r in res)
+                    finish(inflight.pop(0))
         while inflight:
-            res = inflight.pop(0).wait()
-            assert all(r["status"] == 0 for r in res)
+            finish(inflight.pop(0))
 
     run_steps(1)                                # creates the device batches of the pipeline
     ctx.barrier()
