@@ -769,10 +769,25 @@ extern "C" int pngloss_b200_batch_scanlines(pngloss_b200_batch *b) {
         }
         b->dscan = (PlScanDev *)(b->scan_slab + o_desc);
         b->oflags = (uint32_t *)(b->scan_slab + o_flags);
+        // any failure below undoes the whole block, so that the next call starts over instead of launching K4 on
+        // a descriptor table that was never uploaded
+        auto undo = [&]() {
+            cudaGetLastError();
+            cudaFree(b->scan_slab);
+            b->scan_slab = nullptr;
+            if (b->hoflags) cudaFreeHost(b->hoflags);
+            b->hoflags = nullptr;
+            for (int k = 0; k < 3; k++) {
+                if (b->ev_scan[k]) cudaEventDestroy(b->ev_scan[k]);
+                b->ev_scan[k] = nullptr;
+            }
+        };
         if (cudaMallocHost((void **)&b->hoflags, n * 4 * sizeof(uint32_t)) != cudaSuccess ||
             cudaEventCreate(&b->ev_scan[0]) != cudaSuccess || cudaEventCreate(&b->ev_scan[1]) != cudaSuccess ||
-            cudaEventCreate(&b->ev_scan[2]) != cudaSuccess)
+            cudaEventCreate(&b->ev_scan[2]) != cudaSuccess) {
+            undo();
             return set_err(ctx, PNGLOSS_B200_OUT_OF_MEMORY, "scanlines: host-side allocation failed");
+        }
         std::vector<PlScanDev> h(n);
         for (size_t i = 0; i < n; i++) {
             h[i].px = b->himgs[i].out;
@@ -782,8 +797,11 @@ extern "C" int pngloss_b200_batch_scanlines(pngloss_b200_batch *b) {
             h[i].width = b->w[i];
             h[i].height = b->h[i];
         }
-        PL_CUDA(ctx, cudaMemcpyAsync(b->dscan, h.data(), n * sizeof(PlScanDev), cudaMemcpyHostToDevice, b->stream));
-        PL_CUDA(ctx, cudaStreamSynchronize(b->stream));   // h goes out of scope
+        if (cudaMemcpyAsync(b->dscan, h.data(), n * sizeof(PlScanDev), cudaMemcpyHostToDevice, b->stream) != cudaSuccess ||
+            cudaStreamSynchronize(b->stream) != cudaSuccess) {   // (h goes out of scope)
+            undo();
+            return set_err(ctx, PNGLOSS_B200_DEVICE_ERROR, "scanlines: descriptor upload failed");
+        }
     }
     PL_CUDA(ctx, cudaMemsetAsync(b->oflags, 0, n * 4 * sizeof(uint32_t), b->stream));
     uint32_t hmin = b->h[0];

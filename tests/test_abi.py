@@ -54,3 +54,23 @@ def test_no_cpu_fallback_without_device():
     rc = pngloss_b200.optimize_with_rows(img, rf, False, 20, 2)
     assert rc == pngloss_b200.DEVICE_ERROR
     assert (img == 7).all() and not rf.any()
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the CPU arm the driver runs beside the GPU arm) on the smallest config: one JSON
+    line with the keys the contract names, on this GPU-less host."""
+    import json
+    import subprocess
+    import sys
+    if not os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so")):
+        pytest.skip("oracle not built")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "1",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["cores"] >= 1
+    assert line["config"]["baseline_config"] == "1" and line["config"]["strength"] == 19
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
