@@ -1160,30 +1160,58 @@ extern "C" int pngloss_b200_optimize_batch(pngloss_b200_ctx *ctx, pngloss_b200_i
 }
 
 // ---- drop-in entry points (reference src/pngloss_image.h) ----------------------------------------------
-static std::mutex g_default_mu;
-static pngloss_b200_ctx *g_default_ctx = nullptr;
+// The reference's entry points carry no context argument, so the library keeps one per calling thread: a context
+// (its own stream - calls from different threads run side by side on the GPU, there is no global lock) and the
+// device batch of the last call, which is reused when the next image has the same size (a command line that
+// walks over a directory of equally sized files, the website's scaled previews) instead of allocating and
+// freeing 2 x 4 bytes per pixel of device memory per call.
+struct PlThreadDefault {
+    pngloss_b200_ctx *ctx = nullptr;
+    pngloss_b200_batch *batch = nullptr;
+    uint32_t w = 0, h = 0;
+    bool failed = false;
+    ~PlThreadDefault() {
+        // the main thread's copy dies at process exit, possibly after the CUDA runtime: then there is nothing to free
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess) return;
+        if (batch) pngloss_b200_batch_destroy(batch);
+        if (ctx) pngloss_b200_ctx_destroy(ctx);
+    }
+};
+static thread_local PlThreadDefault t_default;
 
 static pngloss_b200_ctx *default_ctx() {
-    if (!g_default_ctx) {
+    PlThreadDefault &d = t_default;
+    if (!d.ctx && !d.failed) {
         int dev = 0;
         if (const char *e = getenv("PNGLOSS_B200_DEVICE")) dev = atoi(e);
-        if (pngloss_b200_ctx_create(&g_default_ctx, dev, nullptr) != PNGLOSS_B200_SUCCESS) {
+        if (pngloss_b200_ctx_create(&d.ctx, dev, nullptr) != PNGLOSS_B200_SUCCESS) {
             fprintf(stderr, "pngloss_b200: no usable CUDA device %d (there is no CPU fallback)\n", dev);
-            return nullptr;
+            d.ctx = nullptr;
+            d.failed = true;
         }
     }
-    return g_default_ctx;
+    return d.ctx;
 }
 
 static int optimize_rows_impl(unsigned char *const *rows, uint32_t width, uint32_t height,
                               unsigned char *row_filters, bool verbose, unsigned strength, long bleed,
                               uint32_t force_bpp = 0) {
-    std::lock_guard<std::mutex> lock(g_default_mu);
     pngloss_b200_ctx *ctx = default_ctx();
     if (!ctx) return PNGLOSS_B200_DEVICE_ERROR;
-    pngloss_b200_batch *b = nullptr;
-    int rc = pngloss_b200_batch_create(ctx, 1, &width, &height, &b);
-    if (rc) return rc;
+    PlThreadDefault &d = t_default;
+    if (d.batch && (d.w != width || d.h != height)) {
+        pngloss_b200_batch_destroy(d.batch);
+        d.batch = nullptr;
+    }
+    int rc = 0;
+    if (!d.batch) {
+        rc = pngloss_b200_batch_create(ctx, 1, &width, &height, &d.batch);
+        if (rc) { d.batch = nullptr; return rc; }
+        d.w = width;
+        d.h = height;
+    }
+    pngloss_b200_batch *b = d.batch;
     int st = 0;
     rc = pngloss_b200_batch_set_mode(b, 0, row_filters == nullptr, force_bpp);
     if (!rc) rc = pngloss_b200_batch_upload_rows(b, 0, rows);
@@ -1202,7 +1230,10 @@ static int optimize_rows_impl(unsigned char *const *rows, uint32_t width, uint32
     }
     if (rc && rc != PNGLOSS_B200_OUT_OF_MEMORY)
         fprintf(stderr, "pngloss_b200: %s\n", pngloss_b200_ctx_error(ctx));
-    pngloss_b200_batch_destroy(b);
+    if (rc) {   // do not keep a batch whose last run failed
+        pngloss_b200_batch_destroy(b);
+        d.batch = nullptr;
+    }
     return rc;
 }
 

@@ -708,3 +708,33 @@ def test_k1_original_histogram_against_the_reference(ctx, oracle):
         packed = np.ascontiguousarray(img[:, :, chans]).reshape(img.shape[0], -1)
         want = ref.original_frequency(packed, bpp) if ref else oracle.original_frequency(packed, bpp)
         assert np.array_equal(folded, want), bpp
+
+
+def test_dropin_calls_reuse_their_batch_and_run_from_threads(oracle):
+    """optimize_with_rows keeps a context and the last device batch per calling thread: repeated calls with the
+    same size, a size change in between, and two threads calling at once must all give the oracle's result."""
+    import threading
+    a = oracle.synth(64, 40, 900)
+    b = oracle.synth(64, 40, 901)
+    c = oracle.synth(52, 33, 902)
+    want = {id(x): oracle.optimize(x, 20, 2, True) for x in (a, b, c)}
+    for img in (a, b, a, c, b):
+        px, rf = run_dropin(img, 20, 2)
+        assert np.array_equal(px, want[id(img)][0]) and np.array_equal(rf, want[id(img)][1])
+    errors = []
+
+    def worker(imgs):
+        try:
+            for _ in range(3):
+                for img in imgs:
+                    px, rf = run_dropin(img, 20, 2)
+                    assert np.array_equal(px, want[id(img)][0]) and np.array_equal(rf, want[id(img)][1])
+        except Exception as e:   # noqa: BLE001
+            errors.append(e)
+
+    ts = [threading.Thread(target=worker, args=(imgs,)) for imgs in ((a, c), (b, a))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
