@@ -1204,23 +1204,26 @@ __device__ __forceinline__ int pl_k4_row_type(const PlScanDev &im, int y, int ro
 }
 
 // Vector path of K4 (width a multiple of 4, so rows are 16-byte aligned): the CTA's rows are cut into
-// segments of 1024 pixels; a thread takes four pixels of a segment = 4 * bpp bytes = bpp whole words of the
-// output stream, which are staged as words; the copy-out realigns the stream to the destination with funnel
+// segments of 256 * PL_K4_PX pixels; a thread takes PL_K4_GROUPS groups of four pixels of a segment, each
+// 4 * bpp bytes = bpp whole words of the output stream, which are staged as words; the copy-out realigns the stream to the destination with funnel
 // shifts and writes 16-byte vectors.  The loads of segment s + 1 are issued before segment s is copied out and
 // the stage is double buffered, so there is one barrier per segment and loads are always in flight.
-#define PL_K4_PX 4
+#ifndef PL_K4_GROUPS
+#define PL_K4_GROUPS 2   /* 4-pixel groups per thread and segment (measured: profiles/r2_k4.txt) */
+#endif
+#define PL_K4_PX (4 * PL_K4_GROUPS)
 #define PL_K4_STAGE_WORDS (PL_K4_THREADS * PL_K4_PX + 8)
 struct PlK4Seg {
-    uint4 c4, u4;        // four pixels of the row and of the row above
-    unsigned left, ul;   // the pixel before them, narrowed
+    uint4 c4[PL_K4_GROUPS], u4[PL_K4_GROUPS];   // the thread's pixels of the row and of the row above
+    unsigned left, ul;                          // the pixel before them, narrowed
 };
 // four pixels' worth of filtered bytes: the filter type is the same for the whole CTA, so the switch is uniform
 template <int BPP, int TYPE>
-__device__ __forceinline__ void pl_k4_filter4(const PlK4Seg &g, unsigned (&r)[4]) {
-    const unsigned cw[4] = {g.c4.x, g.c4.y, g.c4.z, g.c4.w}, uw[4] = {g.u4.x, g.u4.y, g.u4.z, g.u4.w};
-    unsigned left = g.left, ul = g.ul;
+__device__ __forceinline__ void pl_k4_filter4(const uint4 &c4, const uint4 &u4, unsigned &left, unsigned &ul,
+                                              unsigned (&r)[4]) {
+    const unsigned cw[4] = {c4.x, c4.y, c4.z, c4.w}, uw[4] = {u4.x, u4.y, u4.z, u4.w};
 #pragma unroll
-    for (int k = 0; k < PL_K4_PX; k++) {
+    for (int k = 0; k < 4; k++) {
         const unsigned cur = pl_k4_narrow(cw[k], BPP), up = pl_k4_narrow(uw[k], BPP);
         r[k] = pl_k4_filter_word(TYPE, BPP, cur, left, up, ul);
         left = cur;
@@ -1237,12 +1240,18 @@ __device__ __forceinline__ void pl_k4_vector_rows(const PlScanDev &im, int first
         const int x = x0 + tid * PL_K4_PX;
         if (y < H && x < W) {
             const uchar4 *row = im.px + (size_t)y * W;
-            g.c4 = *(const uint4 *)(row + x);
+            // (the width is a multiple of 4, so a thread's 4-pixel groups are either whole or beyond the row)
+#pragma unroll
+            for (int k = 0; k < PL_K4_GROUPS; k++)
+                g.c4[k] = x + 4 * k < W ? *(const uint4 *)(row + x + 4 * k) : make_uint4(0u, 0u, 0u, 0u);
             g.left = x ? pl_k4_narrow(pl_u32(row[x - 1]), BPP) : 0u;
-            g.u4 = make_uint4(0u, 0u, 0u, 0u);
             g.ul = 0u;
+#pragma unroll
+            for (int k = 0; k < PL_K4_GROUPS; k++) g.u4[k] = make_uint4(0u, 0u, 0u, 0u);
             if (y) {
-                g.u4 = *(const uint4 *)(row - W + x);
+#pragma unroll
+                for (int k = 0; k < PL_K4_GROUPS; k++)
+                    if (x + 4 * k < W) g.u4[k] = *(const uint4 *)(row - W + x + 4 * k);
                 g.ul = x ? pl_k4_narrow(pl_u32(row[x - 1 - W]), BPP) : 0u;
             }
         }
@@ -1256,27 +1265,31 @@ __device__ __forceinline__ void pl_k4_vector_rows(const PlScanDev &im, int first
         unsigned *stage_w = stage[buf];
         unsigned char *dst_row = im.scan + (size_t)y * stride;
         if (x0 == 0 && tid == 0) dst_row[0] = (unsigned char)type;
-        if (tid * PL_K4_PX < npx) {
-            unsigned r[4];
-            switch (type) {
-            case 0: pl_k4_filter4<BPP, 0>(seg, r); break;
-            case 1: pl_k4_filter4<BPP, 1>(seg, r); break;
-            case 2: pl_k4_filter4<BPP, 2>(seg, r); break;
-            case 3: pl_k4_filter4<BPP, 3>(seg, r); break;
-            default: pl_k4_filter4<BPP, 4>(seg, r); break;
-            }
-            unsigned *sp = stage_w + tid * BPP;
-            if (BPP == 4) {
-                *(uint4 *)sp = make_uint4(r[0], r[1], r[2], r[3]);
-            } else if (BPP == 3) {
-                sp[0] = r[0] | (r[1] << 24);
-                sp[1] = (r[1] >> 8) | (r[2] << 16);
-                sp[2] = (r[2] >> 16) | (r[3] << 8);
-            } else if (BPP == 2) {
-                sp[0] = r[0] | (r[1] << 16);
-                sp[1] = r[2] | (r[3] << 16);
-            } else {
-                sp[0] = r[0] | (r[1] << 8) | (r[2] << 16) | (r[3] << 24);
+        unsigned left = seg.left, ul = seg.ul;
+#pragma unroll
+        for (int k = 0; k < PL_K4_GROUPS; k++) {
+            if (tid * PL_K4_PX + 4 * k < npx) {
+                unsigned r[4];
+                switch (type) {
+                case 0: pl_k4_filter4<BPP, 0>(seg.c4[k], seg.u4[k], left, ul, r); break;
+                case 1: pl_k4_filter4<BPP, 1>(seg.c4[k], seg.u4[k], left, ul, r); break;
+                case 2: pl_k4_filter4<BPP, 2>(seg.c4[k], seg.u4[k], left, ul, r); break;
+                case 3: pl_k4_filter4<BPP, 3>(seg.c4[k], seg.u4[k], left, ul, r); break;
+                default: pl_k4_filter4<BPP, 4>(seg.c4[k], seg.u4[k], left, ul, r); break;
+                }
+                unsigned *sp = stage_w + (tid * PL_K4_GROUPS + k) * BPP;
+                if (BPP == 4) {
+                    *(uint4 *)sp = make_uint4(r[0], r[1], r[2], r[3]);
+                } else if (BPP == 3) {
+                    sp[0] = r[0] | (r[1] << 24);
+                    sp[1] = (r[1] >> 8) | (r[2] << 16);
+                    sp[2] = (r[2] >> 16) | (r[3] << 8);
+                } else if (BPP == 2) {
+                    sp[0] = r[0] | (r[1] << 16);
+                    sp[1] = r[2] | (r[3] << 16);
+                } else {
+                    sp[0] = r[0] | (r[1] << 8) | (r[2] << 16) | (r[3] << 24);
+                }
             }
         }
         if (tid == 0) stage_w[len >> 2] = 0u;   // the word after the stream (read by the last shift)
