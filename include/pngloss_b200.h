@@ -86,6 +86,12 @@ int pngloss_b200_ctx_set_bucket_maxima(pngloss_b200_ctx *ctx, int mode);
  * same, but only for grids of more than two CTAs per SM (where it is the faster one), 0 = always the generic
  * kernel.  A tuning knob, results never depend on it. */
 int pngloss_b200_ctx_set_lean(pngloss_b200_ctx *ctx, int mode);
+/* Kernel variant for batches small enough that every image gets a CTA (and an SM) of its own - a single image above
+ * all, the reference's one-file-per-call use (src/pngloss.c:173-205,266): the latency kernel (warp-specialised: chain /
+ * producer / post warps) where the winner table exists (15 <= strength <= 126).  1 = one chain warp for the five
+ * filter candidates, 2 = one chain warp per candidate, -1 = the library's choice, 0 = never.  A tuning knob,
+ * results never depend on it. */
+int pngloss_b200_ctx_set_solo(pngloss_b200_ctx *ctx, int mode);
 /* CUDA-event stopwatch on the context's stream (what bench.py times with). */
 int pngloss_b200_ctx_timer_start(pngloss_b200_ctx *ctx);
 int pngloss_b200_ctx_timer_stop(pngloss_b200_ctx *ctx, float *milliseconds);

@@ -28,7 +28,7 @@ EXPORTS = [
     "optimize_with_rows", "optimize_with_stride", "optimizeForAverageFilter", "optimize_image",
     "pngloss_b200_device_count", "pngloss_b200_ctx_create", "pngloss_b200_ctx_destroy",
     "pngloss_b200_ctx_error", "pngloss_b200_ctx_set_lanes", "pngloss_b200_ctx_set_bucket_maxima",
-    "pngloss_b200_ctx_set_lean", "pngloss_b200_ctx_timer_start",
+    "pngloss_b200_ctx_set_lean", "pngloss_b200_ctx_set_solo", "pngloss_b200_ctx_timer_start",
     "pngloss_b200_ctx_timer_stop", "pngloss_b200_ctx_sync", "pngloss_b200_host_alloc",
     "pngloss_b200_host_free", "pngloss_b200_optimize_batch", "pngloss_b200_submit", "pngloss_b200_wait",
     "pngloss_b200_batch_create", "pngloss_b200_batch_create_ex",
@@ -123,6 +123,7 @@ def load_library() -> ctypes.CDLL:
     L.pngloss_b200_ctx_set_lanes.argtypes = [vp, i32]
     L.pngloss_b200_ctx_set_bucket_maxima.argtypes = [vp, i32]
     L.pngloss_b200_ctx_set_lean.argtypes = [vp, i32]
+    L.pngloss_b200_ctx_set_solo.argtypes = [vp, i32]
     L.pngloss_b200_ctx_timer_start.argtypes = [vp]
     L.pngloss_b200_ctx_timer_stop.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     L.pngloss_b200_ctx_sync.argtypes = [vp]
@@ -252,6 +253,11 @@ class Context:
     def set_lean(self, mode: int):
         """1: the lean kernel wherever it applies, -1 (default): only for grids beyond two CTAs per SM, 0: never"""
         self._check(self.lib.pngloss_b200_ctx_set_lean(self.handle, mode))
+
+    def set_solo(self, mode: int):
+        """The latency kernel for one-image-per-CTA grids: 1 one chain warp, 2 five chain warps, -1 library's choice,
+        0 never."""
+        self._check(self.lib.pngloss_b200_ctx_set_solo(self.handle, mode))
 
     # ---- multi-GPU: the library's own NCCL communicator (pl_comm.cuh) --------------------------------------
     def comm_init_rank(self, nranks: int, rank: int, unique_id: bytes):
@@ -473,7 +479,7 @@ class Batch:
         info = (ctypes.c_uint32 * 4)()
         self.ctx._check(self.lib.pngloss_b200_batch_launch_info(self.handle, info))
         return dict(k2_ctas=info[0], images_per_cta=info[1], k2_smem_bytes=info[2], launches=info[3] & 0xff,
-                    bucket_maxima=bool(info[3] & 0x100), lean=bool(info[3] & 0x200))
+                    bucket_maxima=bool(info[3] & 0x100), lean=bool(info[3] & 0x200), solo=bool(info[3] & 0x400))
 
     def scanlines(self):
         """K4: filtered PNG scanlines of the results, on the device (asynchronous)."""

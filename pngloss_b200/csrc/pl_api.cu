@@ -26,6 +26,8 @@ struct pngloss_b200_ctx {
     int bm = -1;   // bucket-maxima variant of K2: -1 choose from the strength, 0 off, 1 on
     int sm_count = 0;
     int lean = -1; // lean kernel (pl_k2_lean) where it applies: -1 yes (default), 0 never, 1 yes
+    int solo = 0;  // latency kernel (pl_k2_solo) for one-image-per-CTA grids: -1 where it applies, 0 never,
+                   // 1 one chain warp, 2 five chain warps
     char err[512] = {0};
     // job API (pngloss_b200_submit / _wait): copy streams, the device batches it recycles, jobs in flight
     cudaStream_t h2d = nullptr, d2h = nullptr;
@@ -178,6 +180,12 @@ extern "C" int pngloss_b200_ctx_set_lanes(pngloss_b200_ctx *ctx, int lpc) {
 extern "C" int pngloss_b200_ctx_set_lean(pngloss_b200_ctx *ctx, int mode) {
     if (!ctx || mode < -1 || mode > 1) return PNGLOSS_B200_INVALID_ARGUMENT;
     ctx->lean = mode;
+    return PNGLOSS_B200_SUCCESS;
+}
+
+extern "C" int pngloss_b200_ctx_set_solo(pngloss_b200_ctx *ctx, int mode) {
+    if (!ctx || mode < -1 || mode > 2) return PNGLOSS_B200_INVALID_ARGUMENT;
+    ctx->solo = mode;
     return PNGLOSS_B200_SUCCESS;
 }
 
@@ -502,6 +510,21 @@ static int launch_k2_lean(pngloss_b200_batch *b, int nblocks, unsigned strength,
     return PNGLOSS_B200_SUCCESS;
 }
 
+// the latency kernel: one image per CTA, chain / producer / post warps (pl_k2_solo.cuh)
+template <int FPW>
+static int launch_k2_solo(pngloss_b200_batch *b, int nblocks, unsigned strength, long bleed) {
+    pngloss_b200_ctx *ctx = b->ctx;
+    const size_t smem = sizeof(PlSoloSmem) + 16;
+    PL_CUDA(ctx, cudaFuncSetAttribute(pl_k2_solo<FPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pl_k2_solo<FPW><<<nblocks, PlSoloCfg<FPW>::THREADS, smem, b->stream>>>(b->dimgs, b->dslots, (int)strength,
+                                                                          (int)bleed);
+    PL_CUDA(ctx, cudaGetLastError());
+    b->info[0] = (uint32_t)nblocks;
+    b->info[1] = 1;
+    b->info[2] = (uint32_t)smem;
+    return PNGLOSS_B200_SUCCESS;
+}
+
 template <int LPC>
 static int launch_k2(pngloss_b200_batch *b, int nblocks, unsigned strength, long bleed, bool bm) {
     return bm ? launch_k2<LPC, true>(b, nblocks, strength, bleed)
@@ -595,8 +618,12 @@ static int launch_run(pngloss_b200_batch *b, unsigned strength, long bleed, int 
     // 2551 Mpx/s at 444 CTAs, 2407 against 2978 at 296): by default only for grids beyond two CTAs per SM
     const bool lean = lpc == 1 && bm && w4 && wmax < PL_BM_MAX_WIDTH &&
                       (ctx->lean > 0 || (ctx->lean < 0 && nblocks > 2 * (ctx->sm_count > 0 ? ctx->sm_count : 148)));
+    // the latency kernel: one image per CTA and a strength the winner table covers
+    const bool table = strength + 1 >= PL_BM_MIN_STEP && strength + 1 <= PL_BM_MAX_STEP && wmax < PL_BM_MAX_WIDTH;
+    const int solo = (lpc == 8 && table && ctx->solo != 0) ? (ctx->solo == 2 ? 1 : 5) : 0;
     int rc;
-    if (lean) rc = launch_k2_lean(b, nblocks, strength, bleed);
+    if (solo) rc = solo == 5 ? launch_k2_solo<5>(b, nblocks, strength, bleed) : launch_k2_solo<1>(b, nblocks, strength, bleed);
+    else if (lean) rc = launch_k2_lean(b, nblocks, strength, bleed);
     else
     switch (lpc) {
     case 8: rc = launch_k2<8>(b, nblocks, strength, bleed, bm); break;
@@ -610,7 +637,7 @@ static int launch_run(pngloss_b200_batch *b, unsigned strength, long bleed, int 
                                                                                     b->batch_hist);
     PL_CUDA(ctx, cudaGetLastError());
     PL_CUDA(ctx, cudaEventRecord(b->ev[3], b->stream));
-    b->info[3] = 3 | (bm ? 0x100u : 0u) | (lean ? 0x200u : 0u);
+    b->info[3] = 3 | ((bm || solo) ? 0x100u : 0u) | ((lean && !solo) ? 0x200u : 0u) | (solo ? 0x400u : 0u);
     b->ran = true;
     return PNGLOSS_B200_SUCCESS;
 }

@@ -1091,6 +1091,7 @@ pl_k2_quantize(const PlImageDev *imgs, const int *slots, int strength, int bleed
 }
 
 #include "pl_k2_lean.cuh"
+#include "pl_k2_solo.cuh"
 
 // --------------------------------------------------------------------------------------------------
 // K3: batch histogram.  out[256] (u64) += sum over images of final_hist.  grid = any, 256 threads.

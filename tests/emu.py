@@ -65,10 +65,11 @@ class Emu:
 
     def counters(self):
         """Sierra taps from the table / computed, channel fix-up replays / skips executed so far (per lane)."""
-        out = (ctypes.c_ulonglong * 8)()
+        out = (ctypes.c_ulonglong * 12)()
         self.lib.emu_counters(out)
         return dict(taps_table=out[0], taps_computed=out[1], fixup_replay=out[2], fixup_skipped=out[3],
-                    bm_lookup=out[4], bm_scan=out[5], bm_fast_update=out[6], bm_general_update=out[7])
+                    bm_lookup=out[4], bm_scan=out[5], bm_fast_update=out[6], bm_general_update=out[7],
+                    solo_fast=out[8], solo_general=out[9])
 
     def synth(self, w, h, seed):
         a = np.zeros((h, w, 4), np.uint8)

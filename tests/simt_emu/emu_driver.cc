@@ -24,8 +24,11 @@ extern "C" int emu_optimize(unsigned char *rgba, int n, uint32_t w, uint32_t h,
                             unsigned long long *batch_hist, uint32_t *chan_hist_out) {
     // lpc: lanes per channel (8, 4, 2, 1), + 16 for the bucket-maxima variant of K2, + 32 for an
     // in-place batch (the output buffer is the input buffer), + 64 for the lean kernel (pl_k2_lean, lpc 1)
+    // + 128 for the latency kernel (pl_k2_solo<5>: one chain warp), + 256 for pl_k2_solo<1> (five chain warps)
     const bool bm = (lpc & 16) != 0, in_place = (lpc & 32) != 0, lean = (lpc & 64) != 0;
+    const int solo = (lpc & 128) ? 5 : (lpc & 256) ? 1 : 0;
     lpc &= 15;
+    if (solo) lpc = 8;   // one image per CTA
     if (lean && (lpc != 1 || (w & 3))) return -2;
     const size_t npx = (size_t)w * h;
     const size_t ew = (size_t)w + PL_ERR_PAD;
@@ -64,7 +67,15 @@ extern "C" int emu_optimize(unsigned char *rgba, int n, uint32_t w, uint32_t h,
     const int nblocks = (n + cpw - 1) / cpw;
     std::vector<int> slots((size_t)nblocks * cpw, -1);
     for (int i = 0; i < n; i++) slots[i] = i;
-    if (lean) {
+    if (solo) {
+        const int *dslots = slots.data();
+        if (solo == 5)
+            simt::launch([&] { pl_k2_solo<5>(dimgs, dslots, strength, bleed); }, dim3(nblocks),
+                         dim3(PlSoloCfg<5>::THREADS), sizeof(PlSoloSmem) + 16);
+        else
+            simt::launch([&] { pl_k2_solo<1>(dimgs, dslots, strength, bleed); }, dim3(nblocks),
+                         dim3(PlSoloCfg<1>::THREADS), sizeof(PlSoloSmem) + 16);
+    } else if (lean) {
         const int *dslots = slots.data();
         simt::launch([&] { pl_k2_lean(dimgs, dslots, strength, bleed); }, dim3(nblocks), dim3(PL_K2_THREADS),
                      sizeof(PlLeanSmem) + PL_L_SMEM_ALIGN);
@@ -112,5 +123,5 @@ extern "C" void emu_synth(unsigned char *dst, uint32_t w, uint32_t h, unsigned l
 
 extern "C" unsigned long long emu_collectives() { return simt::n_collectives; }
 
-unsigned long long pl_emu_counters[8] = {0};
+unsigned long long pl_emu_counters[12] = {0};
 extern "C" void emu_counters(unsigned long long *out) { memcpy(out, pl_emu_counters, sizeof pl_emu_counters); }

@@ -665,6 +665,93 @@ def test_lean_kernel_4k_golden_24_images(ctx, oracle):
     ctx.set_lean(-1)
 
 
+# ---- the latency kernel (pl_k2_solo.cuh) -------------------------------------------------------------------------
+@pytest.mark.parametrize("solo", [1, 2], ids=["one-chain-warp", "five-chain-warps"])
+def test_solo_kernel_golden_and_random(ctx, oracle, solo):
+    """The latency kernel (pl_k2_solo: one image per CTA, chain / producer / post warps, fast path + general path)
+    against the reference's goldens - every small and medium vector whose strength has a winner table, through the
+    drop-in entry and in batches - and against the oracle on random images of every mode (noise, transparent
+    holes, few grey levels, dark and bright: the clamped bands and the channel replay)."""
+    ctx.set_lanes(8)
+    ctx.set_solo(solo)
+    ran = 0
+    for c in cases("small", "medium"):
+        if not 15 <= c["strength"] <= 126:
+            continue
+        img = load_input(c, oracle).copy()
+        rf = np.zeros(img.shape[0], np.uint8) if c["filters"] else None
+        res, = ctx.optimize_batch([img], [rf], c["strength"], c["bleed"])
+        assert res["status"] == 0
+        assert sha16(img) == c["px_sha"], case_id(c)
+        if c["filters"]:
+            assert sha16(rf) == c["filt_sha"], case_id(c)
+        ran += 1
+    assert ran >= 20
+    rng = np.random.default_rng(199)
+    for (w, h, s, b) in [(64, 40, 20, 2), (101, 17, 19, 1), (37, 33, 63, 3), (260, 9, 126, 2), (48, 12, 15, 2),
+                         (300, 20, 85, 2), (31, 50, 40, 1)]:
+        n = 10
+        imgs = []
+        for i in range(n):
+            kind = i % 5
+            if kind == 0:
+                a = oracle.synth(w, h, 500 + i)
+            elif kind == 1:
+                a = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+                a[rng.random((h, w)) < 0.2, 3] = 0
+            elif kind == 2:
+                a = (rng.integers(0, 6, (h, w, 4)) * 51).astype(np.uint8)
+            elif kind == 3:
+                a = rng.integers(0, 30, (h, w, 4)).astype(np.uint8)
+            else:
+                a = (255 - rng.integers(0, 30, (h, w, 4))).astype(np.uint8)
+            imgs.append(to_bpp(a, 4 if i < 5 else (i % 4) + 1))
+        batch = pngloss_b200.Batch(ctx, [w] * n, [h] * n, in_place=bool(w & 1))
+        for i, a in enumerate(imgs):
+            batch.upload(i, a)
+        batch.run(s, b)
+        st, _, _ = batch.finish()
+        assert (st == 0).all()
+        info = batch.launch_info()
+        assert info["solo"] and info["images_per_cta"] == 1
+        out = np.zeros((h, w, 4), np.uint8)
+        rf = np.zeros(h, np.uint8)
+        for i, a in enumerate(imgs):
+            batch.download(i, out, rf)
+            ctx.sync()
+            px, want_rf = oracle.optimize(a, s, b, True)
+            assert np.array_equal(out, px) and np.array_equal(rf, want_rf), (w, h, s, b, i)
+        batch.close()
+    # NULL filters (every row adaptive: the retry path, also below the table's strength range)
+    tiny = [to_bpp(rng.integers(0, 256, (3, 8, 4), dtype=np.uint8), int(rng.integers(1, 5))) for _ in range(24)]
+    outs = [t.copy() for t in tiny]
+    res = ctx.optimize_batch(outs, [None] * len(tiny), 20, 2)
+    for t, o, r in zip(tiny, outs, res):
+        px, _ = oracle.optimize(t, 20, 2, False)
+        assert r["status"] == 0 and np.array_equal(o, px)
+    ctx.set_lanes(0)
+    ctx.set_solo(0)
+
+
+@pytest.mark.parametrize("solo", [1, 2], ids=["one-chain-warp", "five-chain-warps"])
+def test_solo_kernel_suite_images(ctx, oracle, solo):
+    """The eight full suite images (tier "suite" goldens of the unmodified reference) through the latency kernel."""
+    ctx.set_lanes(8)
+    ctx.set_solo(solo)
+    cs = [c for c in cases("suite") if 15 <= c["strength"] <= 126]
+    assert cs
+    for c in cs:
+        img = load_input(c, oracle).copy()
+        rf = np.zeros(img.shape[0], np.uint8) if c["filters"] else None
+        res, = ctx.optimize_batch([img], [rf], c["strength"], c["bleed"])
+        assert res["status"] == 0
+        assert sha16(img) == c["px_sha"], case_id(c)
+        if c["filters"]:
+            assert sha16(rf) == c["filt_sha"], case_id(c)
+    ctx.set_lanes(0)
+    ctx.set_solo(0)
+
+
 def test_full_8192x8192_golden(ctx, oracle):
     """BASELINE configs[4]'s image size in full: one 8192 x 8192 synthetic image (seed 1000, strength 20) through
     the device-resident batch must hash to what the unmodified reference produced (tier "huge" golden, made by

@@ -303,3 +303,74 @@ def test_emu_lean_full_rgba_ctas(emu, oracle):
         imgs.append(n)
     compare(emu, oracle, imgs, 20, 2, False, LEAN)
     compare(emu, oracle, imgs, 31, 1, True, LEAN)
+
+
+# ---- the latency kernel (pl_k2_solo.cuh): one image per CTA, chain / producer / post warps ----------------------
+SOLO5 = 128   # emu flag: pl_k2_solo<5> (one chain warp carries the five candidates)
+SOLO1 = 256   # emu flag: pl_k2_solo<1> (one chain warp per candidate)
+
+SOLO_CASES = CASES + [
+    (32, 3, 31, 4, 20, 2, False),    # exactly one tile: the error rows' four extra cells need a tile of their own
+    (29, 4, 33, 4, 20, 2, False),    # ... or fit the last tile (28 < 29 + 4 = 33 > 32: they do not)
+    (28, 4, 35, 4, 20, 2, False),    # 28 + 4 = 32: they just fit
+    (161, 5, 37, 4, 20, 2, False),   # more tiles than ring stages
+    (130, 3, 39, 3, 63, 1, True),
+    (132, 4, 23, 4, 126, 2, False),  # the largest strength with a table
+    (100, 5, 13, 4, 85, 1, True),
+]
+
+
+@pytest.mark.parametrize("flag", [SOLO5, SOLO1], ids=["one-chain-warp", "five-chain-warps"])
+@pytest.mark.parametrize("case", SOLO_CASES, ids=lambda c: "w%d-h%d-seed%d-bpp%d-s%d-b%d-null%d" % c)
+def test_emu_solo_single_image(emu, oracle, case, flag):
+    w, h, seed, bpp, s, b, nf = case
+    img = to_bpp(oracle.synth(w, h, seed), bpp)
+    got = compare(emu, oracle, [img], s, b, nf, flag)
+    assert got["status"][0][1] == bpp or (w * h == 1)
+
+
+@pytest.mark.parametrize("flag", [SOLO5, SOLO1, IN_PLACE + SOLO5, IN_PLACE + SOLO1])
+def test_emu_solo_batch_mixed_modes(emu, oracle, flag):
+    imgs = [to_bpp(oracle.synth(70, 6, 100 + i), (i % 4) + 1) for i in range(6)]
+    compare(emu, oracle, imgs, 20, 2, False, flag)
+
+
+@pytest.mark.parametrize("flag", [SOLO5, SOLO1])
+def test_emu_solo_retry_path(emu, oracle, flag):
+    rng = np.random.default_rng(7)
+    imgs, retried = [], 0
+    while len(imgs) < 12:
+        img = rng.integers(0, 256, (3, 8, 4), dtype=np.uint8)
+        img = to_bpp(img, int(rng.integers(1, 5)))
+        _, _, tr = oracle.optimize(img, 20, 2, False, trace=True)
+        hit = bool((tr["row_strength"] != 20).any())
+        if hit or len(imgs) % 2 == 1:
+            imgs.append(img)
+            retried += hit
+    assert retried >= 4
+    got = compare(emu, oracle, imgs, 20, 2, True, flag)
+    assert (got["status"][:, 2] > 0).sum() == retried
+
+
+@pytest.mark.parametrize("flag", [SOLO5, SOLO1])
+def test_emu_solo_noise_ties_and_paths(emu, oracle, flag):
+    """Frequency ties, noise (the seam), fully transparent pixels, clamped bands; the look-up, the scan, both bucket
+    updates, the fix-up replay and both tap paths must all have run."""
+    before = emu.counters()
+    rng = np.random.default_rng(11)
+    few = (rng.integers(0, 4, (6, 40, 4)) * 85).astype(np.uint8)
+    noise = rng.integers(0, 256, (6, 40, 4), dtype=np.uint8)
+    holes = noise.copy()
+    holes[rng.random((6, 40)) < 0.3, 3] = 0
+    dark = (rng.integers(0, 30, (6, 40, 4))).astype(np.uint8)
+    bright = (255 - rng.integers(0, 30, (6, 40, 4))).astype(np.uint8)
+    smooth = oracle.synth(40, 6, 5)
+    imgs = [few, noise, holes, to_bpp(holes, 2), dark, bright, smooth, to_bpp(noise, 1), to_bpp(dark, 3)]
+    for s, b, nf in ((19, 2, False), (15, 1, False), (63, 3, True), (126, 2, False), (200, 1, True)):
+        compare(emu, oracle, imgs, s, b, nf, flag)
+    after = emu.counters()
+    for key in ("bm_lookup", "bm_scan", "fixup_replay", "fixup_skipped", "taps_table", "solo_fast", "solo_general"):
+        assert after[key] > before[key], key
+    wide = (np.random.default_rng(99).integers(0, 6, (2, 256, 4)) * 51).astype(np.uint8)
+    for s in (126, 120, 100):
+        compare(emu, oracle, [wide], s, 2, False, flag)

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--lanes", default="8,4,2,1")
     ap.add_argument("--bm", default="-1", help="bucket-maxima modes to sweep: -1 library default, 0 off, 1 on")
     ap.add_argument("--lean", default="-1", help="lean-kernel modes to sweep: -1 library default, 0 generic kernel, 1 lean")
+    ap.add_argument("--solo", default="0", help="latency-kernel modes to sweep: 0 off, 1 one chain warp, 2 five chain warps")
     ap.add_argument("--strength", type=int, default=20)
     ap.add_argument("--reps", type=int, default=1)
     ap.add_argument("--profile", action="store_true", help="with a -DPL_K2_PROFILE build: per-filter busy cycles")
@@ -28,8 +29,9 @@ def main():
         for i in range(n):
             batch.synth(i, 4 + i)
         ctx.sync()
-        for lanes, bm, lean in [(int(x), int(m), int(l)) for x in a.lanes.split(",") for m in a.bm.split(",")
-                                for l in a.lean.split(",")]:
+        for lanes, bm, lean, solo in [(int(x), int(m), int(l), int(so)) for x in a.lanes.split(",")
+                                      for m in a.bm.split(",") for l in a.lean.split(",") for so in a.solo.split(",")]:
+            ctx.set_solo(solo)
             ctx.set_lanes(lanes)
             ctx.set_bucket_maxima(bm)
             ctx.set_lean(lean)
@@ -48,7 +50,7 @@ def main():
                                   "total_kcycles": int(h0[10]),
                                   "busy_frac": [round(b / max(1, int(h0[10])), 3) for b in busy]}), flush=True)
             px = n * a.width * a.height
-            print(json.dumps({"images": n, "w": a.width, "h": a.height, "lanes": lanes, "bm": bm, "lean": lean,
+            print(json.dumps({"images": n, "w": a.width, "h": a.height, "lanes": lanes, "bm": bm, "lean": lean, "solo_mode": solo,
                               "k1_ms": round(best["k1_hist_ms"], 3), "k2_ms": round(best["k2_quantize_ms"], 3),
                               "k2_mpx_s": round(px / best["k2_quantize_ms"] / 1e3, 1),
                               "k1_gpx_s": round(px / best["k1_hist_ms"] / 1e6, 2),
