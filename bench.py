@@ -451,8 +451,8 @@ def main():
                    if small else f"inputs {n * img_bytes / 1e9:.1f} GB per GPU >> 126 MB L2, no flush needed"),
             "device_batch": ("in place; the step re-creates its inputs with the generator kernel first"
                              if in_place else "separate input and output buffers"),
-            "k2_kernel": "pl_k2_lean" if info.get("lean") else "pl_k2_quantize",
-            "k2_lanes_per_channel": 8 // images_per_cta,
+            "k2_kernel": "pl_k2_solo" if info.get("solo") else "pl_k2_lean" if info.get("lean") else "pl_k2_quantize",
+            "k2_lanes_per_channel": 1 if info.get("solo") else 8 // images_per_cta,
             "k2_candidate_choice": "bucket maxima" if info["bucket_maxima"] else "scan",
             "k2_ctas": info["k2_ctas"], "k2_smem_bytes": info["k2_smem_bytes"],
             "collective": ("nccl all_reduce 256 x u64 per step, issued by the library "
@@ -505,7 +505,7 @@ def latency_bound(info, n, w, h, k2_s, sm_mhz):
     """What bounds K2.  Every image is w*h dependent pixel steps per filter candidate; all
     images resident on the SMs advance together, so K2's time = waves x (w*h) x the wall-clock cost of one step,
     and throughput = images in flight / that cost."""
-    ctas_per_sm = 3 if info.get("lean") else {8: 2, 4: 3}.get(info["images_per_cta"], 4)
+    ctas_per_sm = 2 if info.get("solo") else 3 if info.get("lean") else {8: 2, 4: 3}.get(info["images_per_cta"], 4)
     resident = 148 * ctas_per_sm
     waves = max(1, -(-info["k2_ctas"] // resident))
     in_flight = min(n, resident * info["images_per_cta"])

@@ -88,9 +88,10 @@ int pngloss_b200_ctx_set_bucket_maxima(pngloss_b200_ctx *ctx, int mode);
 int pngloss_b200_ctx_set_lean(pngloss_b200_ctx *ctx, int mode);
 /* Kernel variant for batches small enough that every image gets a CTA (and an SM) of its own - a single image above
  * all, the reference's one-file-per-call use (src/pngloss.c:173-205,266): the latency kernel (warp-specialised: chain /
- * producer / post warps) where the winner table exists (15 <= strength <= 126).  1 = one chain warp for the five
- * filter candidates, 2 = one chain warp per candidate, -1 = the library's choice, 0 = never.  A tuning knob,
- * results never depend on it. */
+ * producer / post warps) where the winner table exists (15 <= strength <= 126).  -1 (default) = for batches of at
+ * most two images per SM, unless a lane mapping was set explicitly; 1 = one chain warp for the five filter candidates,
+ * 2 = one chain warp per candidate (both: whenever the lane mapping is 0 or 8); 0 = never.  A tuning knob, results
+ * never depend on it. */
 int pngloss_b200_ctx_set_solo(pngloss_b200_ctx *ctx, int mode);
 /* CUDA-event stopwatch on the context's stream (what bench.py times with). */
 int pngloss_b200_ctx_timer_start(pngloss_b200_ctx *ctx);

@@ -26,7 +26,7 @@ struct pngloss_b200_ctx {
     int bm = -1;   // bucket-maxima variant of K2: -1 choose from the strength, 0 off, 1 on
     int sm_count = 0;
     int lean = -1; // lean kernel (pl_k2_lean) where it applies: -1 yes (default), 0 never, 1 yes
-    int solo = 0;  // latency kernel (pl_k2_solo) for one-image-per-CTA grids: -1 where it applies, 0 never,
+    int solo = -1; // latency kernel (pl_k2_solo) for one-image-per-CTA grids: -1 where it applies (default), 0 never,
                    // 1 one chain warp, 2 five chain warps
     char err[512] = {0};
     // job API (pngloss_b200_submit / _wait): copy streams, the device batches it recycles, jobs in flight
@@ -516,8 +516,8 @@ static int launch_k2_solo(pngloss_b200_batch *b, int nblocks, unsigned strength,
     pngloss_b200_ctx *ctx = b->ctx;
     const size_t smem = sizeof(PlSoloSmem) + 16;
     PL_CUDA(ctx, cudaFuncSetAttribute(pl_k2_solo<FPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pl_k2_solo<FPW><<<nblocks, PlSoloCfg<FPW>::THREADS, smem, b->stream>>>(b->dimgs, b->dslots, (int)strength,
-                                                                          (int)bleed);
+    pl_k2_solo<FPW><<<nblocks, PlSoloCfg<FPW>::THREADS, smem, b->stream>>>(
+        b->dimgs, b->dslots, (int)strength, (int)bleed, (unsigned)(ctx->sm_count > 0 ? ctx->sm_count : 148));
     PL_CUDA(ctx, cudaGetLastError());
     b->info[0] = (uint32_t)nblocks;
     b->info[1] = 1;
@@ -542,6 +542,21 @@ static int choose_lpc(const pngloss_b200_batch *b) {
     return per_cta <= 1 ? 8 : per_cta <= 2 ? 4 : per_cta <= 4 ? 2 : 1;
 }
 
+// The latency kernel (pl_k2_solo.cuh: 3.0 against 2.0 Mpx/s per image, profiles/r2_sweep_solo.txt) takes a batch when
+// every image can have a CTA of its own with at most two CTAs per SM (its 123 registers x 256 threads allow two), and
+// the strength has a winner table.  0 = no, 5 / 1 = filter candidates per chain warp.  An explicit lane mapping
+// (pngloss_b200_ctx_set_lanes) keeps the generic kernel unless the latency kernel is asked for explicitly.
+static int use_solo(const pngloss_b200_batch *b, unsigned strength) {
+    const pngloss_b200_ctx *ctx = b->ctx;
+    uint32_t wmax = 0;
+    for (size_t i = 0; i < b->n; i++) wmax = std::max(wmax, b->w[i]);
+    const bool table = strength + 1 >= PL_BM_MIN_STEP && strength + 1 <= PL_BM_MAX_STEP && wmax < PL_BM_MAX_WIDTH;
+    if (!table || ctx->solo == 0) return 0;
+    if (ctx->solo > 0) return (ctx->lpc == 0 || ctx->lpc == 8) ? (ctx->solo == 2 ? 1 : 5) : 0;
+    const size_t sms = ctx->sm_count > 0 ? (size_t)ctx->sm_count : 148;
+    return (ctx->lpc == 0 && b->n <= 2 * sms) ? 5 : 0;
+}
+
 // Host-side part of a run: CTA packing, descriptors and the cleared accumulators, enqueued on `stream`
 // (the batch's own stream, or the job API's upload stream).
 static int prepare_run(pngloss_b200_batch *b, unsigned strength, long bleed, cudaStream_t stream, int *lpc_out,
@@ -551,7 +566,7 @@ static int prepare_run(pngloss_b200_batch *b, unsigned strength, long bleed, cud
     if (strength > 255 || bleed < 1 || bleed > 32767)
         return set_err(ctx, PNGLOSS_B200_INVALID_ARGUMENT, "strength 0..255, bleed 1..32767");
     PL_CUDA(ctx, cudaSetDevice(ctx->device));
-    const int lpc = choose_lpc(b);
+    const int lpc = use_solo(b, strength) ? 8 : choose_lpc(b);
     const int cpw = 8 / lpc;
     // pack equally sized images into CTAs of cpw slots
     b->hslots.clear();
@@ -618,9 +633,7 @@ static int launch_run(pngloss_b200_batch *b, unsigned strength, long bleed, int 
     // 2551 Mpx/s at 444 CTAs, 2407 against 2978 at 296): by default only for grids beyond two CTAs per SM
     const bool lean = lpc == 1 && bm && w4 && wmax < PL_BM_MAX_WIDTH &&
                       (ctx->lean > 0 || (ctx->lean < 0 && nblocks > 2 * (ctx->sm_count > 0 ? ctx->sm_count : 148)));
-    // the latency kernel: one image per CTA and a strength the winner table covers
-    const bool table = strength + 1 >= PL_BM_MIN_STEP && strength + 1 <= PL_BM_MAX_STEP && wmax < PL_BM_MAX_WIDTH;
-    const int solo = (lpc == 8 && table && ctx->solo != 0) ? (ctx->solo == 2 ? 1 : 5) : 0;
+    const int solo = lpc == 8 ? use_solo(b, strength) : 0;
     int rc;
     if (solo) rc = solo == 5 ? launch_k2_solo<5>(b, nblocks, strength, bleed) : launch_k2_solo<1>(b, nblocks, strength, bleed);
     else if (lean) rc = launch_k2_lean(b, nblocks, strength, bleed);

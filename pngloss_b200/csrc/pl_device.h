@@ -217,6 +217,11 @@ __device__ __forceinline__ void pl_atoms_max32(PlSh a, uint32_t v) {
     if (v > *(volatile uint32_t *)a) *(volatile uint32_t *)a = v;
 }
 __device__ __forceinline__ void pl_atoms_add32(PlSh a, uint32_t v) { *(volatile uint32_t *)a += v; }
+__device__ __forceinline__ uint32_t pl_atoms_add32_ret(PlSh a, uint32_t v) {
+    const uint32_t o = *(volatile uint32_t *)a;
+    *(volatile uint32_t *)a = o + v;
+    return o;
+}
 #else
 typedef unsigned PlSh;
 __device__ __forceinline__ PlSh pl_sh(void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -254,6 +259,12 @@ __device__ __forceinline__ void pl_atoms_max32(PlSh a, uint32_t v) {
 // with 0 are no-ops
 __device__ __forceinline__ void pl_atoms_add32(PlSh a, uint32_t v) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+// ... returning the value before the addition
+__device__ __forceinline__ uint32_t pl_atoms_add32_ret(PlSh a, uint32_t v) {
+    uint32_t o;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory");
+    return o;
 }
 #endif
 

@@ -31,27 +31,40 @@
 #ifndef PL_S_STAGES
 #define PL_S_STAGES 4      // tiles in the rings (post warps release a tile one tile late: >= 3)
 #endif
+#ifndef PL_S_ONEVOTE
+#define PL_S_ONEVOTE 0     // measured (profiles/r2_solo_variants.txt)
+#endif
+#ifndef PL_S_MIN_BLOCKS
+#define PL_S_MIN_BLOCKS(FPW) ((FPW) == 5 ? 2 : 1)   // FPW = 5: 128 registers, two CTAs (two images) per SM
+#endif
 #define PL_S_TAPC_HALF 512 // the chain's tap table covers differences -512 .. 511
 #define PL_S_BOFF 1024     // the band table covers here - predicted = -1024 .. 1023
 #define PL_S_HPAD 4        // entries between the candidates' histograms (bank stagger)
 #define PL_S_BM_ROW (PL_BM_MAX + 2)
 #define PL_S_POSTW PL_FILTERS
 
-// Warp roles.  The hardware arbiter prefers the higher warp id of a sub-partition (warp id % 4), so the chain warps
-// are the last ones; FPW = 5: warps 0 producer, 1 2 4 5 6 post, 3 idles (it shares the chain warp's sub-partition),
-// 7 chain.  FPW = 1: warps 0 producer, 1 .. 5 post, 6 idle, 7 .. 11 chain.
+// Warp roles.  The hardware arbiter prefers the higher warp id of a sub-partition (warp id % 4), so a chain warp is the
+// higher warp of its sub-partition.  FPW = 5 (8 warps): the chain warp is warp 4 + r and warp r idles at the CTA
+// barriers, so that the chain has the scheduler of sub-partition r to itself; r rotates with the CTA index (wave
+// number), so that the chain warps of the CTAs that share an SM sit on different schedulers.  The other six warps
+// are, in ascending order, the producer and the five post warps.  FPW = 1 (12 warps): warps 0 producer, 1 .. 5 post,
+// 6 idle, 7 .. 11 chain.
 template <int FPW>
 struct PlSoloCfg {
     static const int NCHAIN = PL_FILTERS / FPW;             // chain warps
     static const int NWARPS = FPW == 5 ? 8 : 12;
     static const int THREADS = 32 * NWARPS;
-    static const int IDLE = FPW == 5 ? 3 : 6;
-    static const int CHAIN0 = NWARPS - NCHAIN;
-    // post warp index (candidate) of a warp, -1 if it is none
-    __device__ static int post_of(int w) {
-        if (w == 0 || w == IDLE || w >= CHAIN0) return -1;
-        return w < IDLE ? w - 1 : w - 2;
+    // role of warp w: -3 idle, -2 chain, -1 producer, 0 .. 4 post warp of that candidate
+    __device__ static int role(int w, int rot) {
+        if (FPW == 5) {
+            if (w == 4 + rot) return -2;
+            if (w == rot) return -3;
+            const int k = w - (w > rot ? 1 : 0) - (w > 4 + rot ? 1 : 0);   // index among the other six
+            return k - 1;
+        }
+        return w == 0 ? -1 : w <= 5 ? w - 1 : w == 6 ? -3 : -2;
     }
+    __device__ static int chain_index(int w) { return FPW == 5 ? 0 : w - 7; }
 };
 
 struct PlSoloSmem {
@@ -129,19 +142,24 @@ __device__ __forceinline__ unsigned pl_solo_band_entry(const PlBm &bmc, int want
 
 // Commit of a byte: count the symbol, and let its new key (count `now`, rank) enter every table entry that holds its
 // bin.  No predicates (they would become branches): an inactive lane (actm = 0) adds 0, a key that must not enter is 0.
+// `three`: some bin of this strength has a third entry (warp-uniform; shared-memory atomics are the expensive part of
+// a commit - they queue in front of the next pixel's loads - so the usual strengths issue two, not three).
 __device__ __forceinline__ void pl_solo_commit(PlSh hk_sh, PlSh bm_sh, PlSh bins_sh, PlSh bins3_sh, int sym, unsigned now,
-                                               unsigned rank7, unsigned actm) {
+                                               unsigned rank7, unsigned actm, bool three) {
     const unsigned bin = (unsigned)sym & 255u;
     const uint4 bi = pl_lds128(bins_sh + bin * 16u);
-    const unsigned long long bj = pl_lds64(bins3_sh + bin * 8u);
+    unsigned long long bj = 0;
+    if (three) bj = pl_lds64(bins3_sh + bin * 8u);
     pl_atoms_add32(hk_sh + bin * 8u + 4u, actm & 1u);
-    const unsigned e2 = (unsigned)bj, b2 = (unsigned)(bj >> 32);
     const unsigned k0 = (((now - bi.y) << PL_BM_COUNT_SHIFT) | rank7 | (bi.x & 127u)) & actm;
     const unsigned k1 = (((now - bi.w) << PL_BM_COUNT_SHIFT) | rank7 | (bi.z & 127u)) & actm;
-    const unsigned k2 = (((now - b2) << PL_BM_COUNT_SHIFT) | rank7 | (e2 & 127u)) & actm;
     pl_atoms_max32(bm_sh + (bi.x >> 16), now >= bi.y ? k0 : 0u);
     pl_atoms_max32(bm_sh + (bi.z >> 16), now >= bi.w ? k1 : 0u);
-    pl_atoms_max32(bm_sh + (e2 >> 16), now >= b2 ? k2 : 0u);
+    if (three) {
+        const unsigned e2 = (unsigned)bj, b2 = (unsigned)(bj >> 32);
+        const unsigned k2 = (((now - b2) << PL_BM_COUNT_SHIFT) | rank7 | (e2 & 127u)) & actm;
+        pl_atoms_max32(bm_sh + (e2 >> 16), now >= b2 ? k2 : 0u);
+    }
 }
 
 // ---- chain warp: the dependent chain of one candidate row (FPW = 1) or of all five (FPW = 5) ------------------
@@ -182,6 +200,10 @@ __device__ __forceinline__ unsigned pl_solo_chain(PlSoloSmem &sm, int f, int ch,
     const int P1 = bmc.P1, N1 = bmc.N1, tz = bmc.P1 + bmc.N1;
     const bool table = try_fast && P1 > 0;
     const bool al = alpha_rule && ch == 3;
+    // a bin has a third table entry where the seam reaches the zero band: last non-negative bucket's wrap >= -q
+    // (measured, profiles/r2_solo_variants.txt: with one chain warp the third, usually idle, atomic is cheaper than
+    // the branch around it; with five chain warps the atomics are what the warps queue for)
+    const bool three = FPW == 5 || (P1 > 0 && bmc.seam_n >= -q);
     // earlier channels of the pixel that are active (the channel order of the fix-up)
     unsigned emask = 0;
 #pragma unroll
@@ -263,8 +285,18 @@ __device__ __forceinline__ unsigned pl_solo_chain(PlSoloSmem &sm, int f, int ch,
                     conflict |= earlier & inb & !same & near;
                     dup += (unsigned)(earlier & same);
                 }
-                const bool any_fail = __any_sync(PL_FULL, act && !ok);
+                const bool fails = act && !ok;
+#if PL_S_ONEVOTE
+                // one vote for the common case; the rare cases are told apart behind it
+                bool any_fail = false, any_conflict = false;
+                if (__any_sync(PL_FULL, fails || conflict)) {
+                    any_fail = __any_sync(PL_FULL, fails);
+                    any_conflict = __any_sync(PL_FULL, conflict);
+                }
+#else
+                const bool any_fail = __any_sync(PL_FULL, fails);
                 const bool any_conflict = __any_sync(PL_FULL, conflict);
+#endif
                 if (!any_fail) {
                     PL_EMU_COUNT(PL_CNT_SOLO_FAST);
                     if (!any_conflict) {
@@ -301,7 +333,7 @@ __device__ __forceinline__ unsigned pl_solo_chain(PlSoloSmem &sm, int f, int ch,
                     }
                     diff = (transp || !act) ? 0 : want - sym;   // = here - back; |diff| <= q: both lie in the band
                     const uint32_t te = pl_lds32(tapc_sh + diff * 4);
-                    pl_solo_commit(hk_sh, bm_sh, bins_sh, bins3_sh, sym, bc + 1u, rk << 7, actm);
+                    pl_solo_commit(hk_sh, bm_sh, bins_sh, bins3_sh, sym, bc + 1u, rk << 7, actm, three);
                     back &= (int)actm;
                     pl_sts32(po + (unsigned)i * 16u, ((unsigned)back & 255u) | ((unsigned)diff << 16));
                     left = back;
@@ -414,7 +446,7 @@ __device__ __forceinline__ unsigned pl_solo_chain(PlSoloSmem &sm, int f, int ch,
                 const int sym = lo + bpos;
                 diff = (act && !transp) ? pl_sext16(want - sym) : 0;   // here - back (0 for a transparent pixel)
                 back = act ? sym + pred : 0;
-                pl_solo_commit(hk_sh, bm_sh, bins_sh, bins3_sh, sym, bc + 1u, (bl >> (PL_KEY_RANK_SHIFT - 7)) & (255u << 7), actm);
+                pl_solo_commit(hk_sh, bm_sh, bins_sh, bins3_sh, sym, bc + 1u, (bl >> (PL_KEY_RANK_SHIFT - 7)) & (255u << 7), actm, three);
             }
 
             pl_sts32(po + (unsigned)i * 16u, ((unsigned)back & 255u) | ((unsigned)diff << 16));
@@ -628,15 +660,17 @@ __device__ __forceinline__ void pl_solo_post(PlSoloSmem &sm, int pf, int chmask,
 }
 
 template <int FPW>
-__global__ void __launch_bounds__(PlSoloCfg<FPW>::THREADS, 1)
-pl_k2_solo(const PlImageDev *imgs, const int *slots, int strength, int bleed) {
+__global__ void __launch_bounds__(PlSoloCfg<FPW>::THREADS, PL_S_MIN_BLOCKS(FPW))
+pl_k2_solo(const PlImageDev *imgs, const int *slots, int strength, int bleed, unsigned sm_count) {
     typedef PlSoloCfg<FPW> C;
     PL_DYN_SMEM(smem_raw);
     PlSoloSmem &sm = *(PlSoloSmem *)pl_align_shared(smem_raw, 16);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int idx = slots[blockIdx.x];
     if (idx < 0) return;
-    const int pf = C::post_of(warp);   // candidate this warp post-processes (-1: none)
+    // (CTAs are placed round-robin over the SMs, so the CTAs that share an SM differ in blockIdx / #SMs)
+    const int role = C::role(warp, (int)((blockIdx.x / sm_count) & 3u));
+    const int pf = role >= 0 ? role : -1;   // candidate this warp post-processes (-1: none)
 
     // ---- set-up ------------------------------------------------------------------------------------------------
     if (tid == 0) {
@@ -744,14 +778,14 @@ pl_k2_solo(const PlImageDev *imgs, const int *slots, int strength, int bleed) {
             __syncthreads();
 
             // ---- the row, by role -----------------------------------------------------------------------------
-            if (warp >= C::CHAIN0) {
-                const int f = FPW == 5 ? lane >> 2 : warp - C::CHAIN0;
+            if (role == -2) {
+                const int f = FPW == 5 ? lane >> 2 : C::chain_index(warp);
                 const bool lane_act = FPW == 5 ? lane < 4 * PL_FILTERS : lane < 4;
                 const unsigned g = pl_solo_chain<FPW>(sm, f, lane & 3, lane_act, chmask, alpha_rule, q, step_magic, W,
                                                       bleed_magic, use, try_fast);
                 // images where the fast path mostly fails skip the attempt (and retry it every 16th row)
                 try_fast = 4u * g <= 3u * (unsigned)W || (y & 15) == 15;
-            } else if (warp == 0) {
+            } else if (role == -1) {
                 pl_solo_producer(sm, W, y, y & 1, prev_w, use);
             } else if (pf >= 0) {
                 pl_solo_post(sm, pf, chmask, W, y, y & 1, prev_w, adaptive, bleed_magic, use);

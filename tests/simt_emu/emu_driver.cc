@@ -70,10 +70,10 @@ extern "C" int emu_optimize(unsigned char *rgba, int n, uint32_t w, uint32_t h,
     if (solo) {
         const int *dslots = slots.data();
         if (solo == 5)
-            simt::launch([&] { pl_k2_solo<5>(dimgs, dslots, strength, bleed); }, dim3(nblocks),
+            simt::launch([&] { pl_k2_solo<5>(dimgs, dslots, strength, bleed, 2u); }, dim3(nblocks),
                          dim3(PlSoloCfg<5>::THREADS), sizeof(PlSoloSmem) + 16);
         else
-            simt::launch([&] { pl_k2_solo<1>(dimgs, dslots, strength, bleed); }, dim3(nblocks),
+            simt::launch([&] { pl_k2_solo<1>(dimgs, dslots, strength, bleed, 2u); }, dim3(nblocks),
                          dim3(PlSoloCfg<1>::THREADS), sizeof(PlSoloSmem) + 16);
     } else if (lean) {
         const int *dslots = slots.data();

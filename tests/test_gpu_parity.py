@@ -730,7 +730,7 @@ def test_solo_kernel_golden_and_random(ctx, oracle, solo):
         px, _ = oracle.optimize(t, 20, 2, False)
         assert r["status"] == 0 and np.array_equal(o, px)
     ctx.set_lanes(0)
-    ctx.set_solo(0)
+    ctx.set_solo(-1)
 
 
 @pytest.mark.parametrize("solo", [1, 2], ids=["one-chain-warp", "five-chain-warps"])
@@ -749,7 +749,7 @@ def test_solo_kernel_suite_images(ctx, oracle, solo):
         if c["filters"]:
             assert sha16(rf) == c["filt_sha"], case_id(c)
     ctx.set_lanes(0)
-    ctx.set_solo(0)
+    ctx.set_solo(-1)
 
 
 def test_full_8192x8192_golden(ctx, oracle):
