@@ -142,21 +142,27 @@ __device__ __forceinline__ unsigned pl_solo_band_entry(const PlBm &bmc, int want
 
 // Commit of a byte: count the symbol, and let its new key (count `now`, rank) enter every table entry that holds its
 // bin.  No predicates (they would become branches): an inactive lane (actm = 0) adds 0, a key that must not enter is 0.
-// `three`: some bin of this strength has a third entry (warp-uniform; shared-memory atomics are the expensive part of
-// a commit - they queue in front of the next pixel's loads - so the usual strengths issue two, not three).
-__device__ __forceinline__ void pl_solo_commit(PlSh hk_sh, PlSh bm_sh, PlSh bins_sh, PlSh bins3_sh, int sym, unsigned now,
+// `three`: some bin of this strength has a third entry (warp-uniform).  The loads are a call of their own: the fast
+// path issues them for its provisional symbol before the channel vote, so that their latency is not exposed.
+struct PlBinLoaded { uint4 bi; unsigned long long bj; };
+__device__ __forceinline__ PlBinLoaded pl_solo_bin_load(PlSh bins_sh, PlSh bins3_sh, int sym, bool three) {
+    const unsigned bin = (unsigned)sym & 255u;
+    PlBinLoaded r;
+    r.bi = pl_lds128(bins_sh + bin * 16u);
+    r.bj = three ? pl_lds64(bins3_sh + bin * 8u) : 0ull;
+    return r;
+}
+__device__ __forceinline__ void pl_solo_commit(PlSh hk_sh, PlSh bm_sh, const PlBinLoaded &ld, int sym, unsigned now,
                                                unsigned rank7, unsigned actm, bool three) {
     const unsigned bin = (unsigned)sym & 255u;
-    const uint4 bi = pl_lds128(bins_sh + bin * 16u);
-    unsigned long long bj = 0;
-    if (three) bj = pl_lds64(bins3_sh + bin * 8u);
+    const uint4 bi = ld.bi;
     pl_atoms_add32(hk_sh + bin * 8u + 4u, actm & 1u);
     const unsigned k0 = (((now - bi.y) << PL_BM_COUNT_SHIFT) | rank7 | (bi.x & 127u)) & actm;
     const unsigned k1 = (((now - bi.w) << PL_BM_COUNT_SHIFT) | rank7 | (bi.z & 127u)) & actm;
     pl_atoms_max32(bm_sh + (bi.x >> 16), now >= bi.y ? k0 : 0u);
     pl_atoms_max32(bm_sh + (bi.z >> 16), now >= bi.w ? k1 : 0u);
     if (three) {
-        const unsigned e2 = (unsigned)bj, b2 = (unsigned)(bj >> 32);
+        const unsigned e2 = (unsigned)ld.bj, b2 = (unsigned)(ld.bj >> 32);
         const unsigned k2 = (((now - b2) << PL_BM_COUNT_SHIFT) | rank7 | (e2 & 127u)) & actm;
         pl_atoms_max32(bm_sh + (e2 >> 16), now >= b2 ? k2 : 0u);
     }
@@ -265,6 +271,11 @@ __device__ __forceinline__ unsigned pl_solo_chain(PlSoloSmem &sm, int f, int ch,
                 int sym = back - pred;
                 unsigned bc = e_wins ? ce : base_l + (be_x >> PL_BM_COUNT_SHIFT);
                 unsigned rk = e_wins ? re : (kw & 255u);
+                // what the commit needs from the tables, for the provisional symbol (it is final unless the channel order
+                // is replayed below): issued here, the loads are back by the time the vote is
+                PlBinLoaded ld = pl_solo_bin_load(bins_sh, bins3_sh, sym, three);
+                diff = (transp || !act) ? 0 : want - sym;   // = here - back; |diff| <= q: both lie in the band
+                uint32_t te = pl_lds32(tapc_sh + diff * 4);
                 // channel order (see pl_row_pass "fix-up"): does a symbol chosen by an earlier channel disturb this one?
                 // The clamped band in symbols is [lo, lo + span]; a bin v lies in it iff ((v - lo) & 255) <= span.
                 const int lob = transp ? 0 : max(bl, 0), hib = transp ? 0 : min(bl + q, 255);
@@ -330,10 +341,11 @@ __device__ __forceinline__ unsigned pl_solo_chain(PlSoloSmem &sm, int f, int ch,
                             }
                         }
                         back = sym + pred;
+                        ld = pl_solo_bin_load(bins_sh, bins3_sh, sym, three);
+                        diff = (transp || !act) ? 0 : want - sym;
+                        te = pl_lds32(tapc_sh + diff * 4);
                     }
-                    diff = (transp || !act) ? 0 : want - sym;   // = here - back; |diff| <= q: both lie in the band
-                    const uint32_t te = pl_lds32(tapc_sh + diff * 4);
-                    pl_solo_commit(hk_sh, bm_sh, bins_sh, bins3_sh, sym, bc + 1u, rk << 7, actm, three);
+                    pl_solo_commit(hk_sh, bm_sh, ld, sym, bc + 1u, rk << 7, actm, three);
                     back &= (int)actm;
                     pl_sts32(po + (unsigned)i * 16u, ((unsigned)back & 255u) | ((unsigned)diff << 16));
                     left = back;
@@ -446,7 +458,8 @@ __device__ __forceinline__ unsigned pl_solo_chain(PlSoloSmem &sm, int f, int ch,
                 const int sym = lo + bpos;
                 diff = (act && !transp) ? pl_sext16(want - sym) : 0;   // here - back (0 for a transparent pixel)
                 back = act ? sym + pred : 0;
-                pl_solo_commit(hk_sh, bm_sh, bins_sh, bins3_sh, sym, bc + 1u, (bl >> (PL_KEY_RANK_SHIFT - 7)) & (255u << 7), actm, three);
+                pl_solo_commit(hk_sh, bm_sh, pl_solo_bin_load(bins_sh, bins3_sh, sym, three), sym, bc + 1u,
+                               (bl >> (PL_KEY_RANK_SHIFT - 7)) & (255u << 7), actm, three);
             }
 
             pl_sts32(po + (unsigned)i * 16u, ((unsigned)back & 255u) | ((unsigned)diff << 16));
