@@ -175,16 +175,19 @@ __device__ __forceinline__ void pl_solo_commit(PlSh hk_sh, PlSh bm_sh, const PlB
 // the whole zero band [-q, 0] ("Z+"): a band [-q, 0] whose symbol 0 is admissible (0 <= predicted <= 255) looks Z+
 // up instead of negative bucket 0, so no second entry has to be merged on the chain.
 //
-// Every pixel first takes the FAST path: straight-line code for the bytes whose answer is the looked-up winner or
-// the exact symbol - the bucket exists and its winner lies inside the clamped band, or the band is the exact symbol
-// alone.  With b = band start + predicted (the band in byte values, [b, b + q]): the winner at position p is
-// admissible iff 0 <= b + p <= 255, the exact symbol iff b <= orig <= b + q, and the chosen byte is b + p or orig.
-// One vote checks that the look-up answered every lane; a second one whether an earlier channel of the pixel
-// disturbs a later one (then the channel order is replayed exactly, still on this path).  If any lane of the warp
-// fails, the warp redoes the pixel on the GENERAL path (the code of pl_lean_row_pass: scan fall-back, general
-// bands).  Both paths give the reference's answer; the fast one only ever commits where it is provably the same.
-// Returns the number of pixels that took the general path (the caller stops trying the fast path on images where
-// it mostly fails).
+// Every pixel takes the FAST path first when the strength has a table: straight-line code for the bytes whose answer
+// is the looked-up winner, the exact symbol, or forced.  With b = band start + predicted (the band in byte values,
+// [b, b + q], clamped to [lob, hib] inside 0 .. 255): the bucket's winner at position p is admissible iff
+// 0 <= b + p <= 255, the exact symbol iff b <= orig <= b + q, and the chosen byte is b + p or orig; a band of one value
+// (cut down to it, collapsed onto 0 or 255, or a fully transparent pixel) needs no table at all.  One vote asks
+// whether every lane got its answer that way, a second one whether an earlier channel of the pixel disturbs a later
+// one (if so the channel order is replayed exactly, still on this path).  If a lane has no answer - a band that the
+// byte range cut short and that lost its bucket's winner that way (saturated regions), a band beyond the table - the
+// warp redoes the pixel on the GENERAL path (the code of pl_lean_row_pass: scan, general bands), which also serves
+// the strengths without a table.  (Letting such a lane scan its band inside the fast path was measured: slower on
+// every image, profiles/r2_solo_variants.txt.)  Both paths give the reference's answer; the fast one only commits
+// where it is provably the same.  Returns the number of pixels that took the general path (the caller stops
+// attempting the fast path on images where it mostly fails).
 template <int FPW>
 __device__ __forceinline__ unsigned pl_solo_chain(PlSoloSmem &sm, int f, int ch, bool lane_act, int chmask,
                                                   bool alpha_rule, int q, unsigned step_magic, int W,
@@ -255,30 +258,35 @@ __device__ __forceinline__ unsigned pl_solo_chain(PlSoloSmem &sm, int f, int ch,
                 const unsigned long long xe64 = pl_lds64(hk_sh + ((unsigned)ex0 & 255u) * 8u);
                 const unsigned t8 = (((unsigned)pred <= 255u) ? (bw >> 8) : bw) & 255u;
                 const unsigned long long be64 = pl_lds64(bm_sh + t8 * 8u);
-                const bool tv = t8 != 255u && (unsigned)(want + PL_S_BOFF) < 2u * PL_S_BOFF;
+                const bool lutok = (unsigned)(want + PL_S_BOFF) < 2u * PL_S_BOFF, tv = t8 != 255u;
                 const int bl = ((int)bw >> 16) + pred;          // the band in byte values: [bl, bl + q]
                 const unsigned be_x = (unsigned)be64, base_l = (unsigned)(be64 >> 32);
                 const int wbyte = bl + 127 - (int)(be_x & 127u);
-                const bool inr = tv && !transp && (unsigned)wbyte <= 255u;
+                // The clamped band in byte values: [lob, hib].  A band that the byte range cuts down to one value - or
+                // that lies outside of it altogether and collapses onto 0 or 255 (:195-210) - has one admissible symbol,
+                // whatever the tables say; so has a fully transparent pixel (its band is {0}).
+                const int lob = transp ? 0 : min(max(bl, 0), 255), hib = transp ? 0 : min(max(bl + q, 0), 255);
+                const bool single = lob == hib;
+                const int fs = lob - pred;                      // ... that symbol
+                const unsigned long long fx64 = pl_lds64(hk_sh + ((unsigned)fs & 255u) * 8u);
+                const bool inr = tv && (unsigned)wbyte <= 255u;
                 // the exact symbol wins against the bucket winner iff its (count, rank) is not smaller (:228-244)
-                const bool fe = transp || (unsigned)(o - bl) <= (unsigned)q;
-                const bool single = bl == 255 || bl + q == 0;
+                const bool fe = (unsigned)(o - bl) <= (unsigned)q;
                 const unsigned ce = (unsigned)(xe64 >> 32), re = (unsigned)xe64 >> PL_KEY_RANK_SHIFT;
                 const unsigned ke = ((ce - base_l) << 8) | re, kw = be_x >> 7;
-                const bool e_wins = fe && (!inr || (ce >= base_l && ke >= kw));
-                const bool ok = inr || (fe && (single || transp));
-                back = e_wins ? o : wbyte;
+                const bool e_wins = fe && ce >= base_l && ke >= kw;
+                back = single ? lob : e_wins ? o : wbyte;
                 int sym = back - pred;
-                unsigned bc = e_wins ? ce : base_l + (be_x >> PL_BM_COUNT_SHIFT);
-                unsigned rk = e_wins ? re : (kw & 255u);
+                unsigned bc = single ? (unsigned)(fx64 >> 32) : e_wins ? ce : base_l + (be_x >> PL_BM_COUNT_SHIFT);
+                unsigned rk = single ? (unsigned)fx64 >> PL_KEY_RANK_SHIFT : e_wins ? re : (kw & 255u);
                 // what the commit needs from the tables, for the provisional symbol (it is final unless the channel order
                 // is replayed below): issued here, the loads are back by the time the vote is
                 PlBinLoaded ld = pl_solo_bin_load(bins_sh, bins3_sh, sym, three);
-                diff = (transp || !act) ? 0 : want - sym;   // = here - back; |diff| <= q: both lie in the band
-                uint32_t te = pl_lds32(tapc_sh + diff * 4);
+                diff = (transp || !act) ? 0 : want - sym;   // = here - back; beyond the band's width only where it collapsed
+                const bool tap_ok = (unsigned)(diff + PL_S_TAPC_HALF) < 2u * PL_S_TAPC_HALF;
+                uint32_t te = pl_lds32(tapc_sh + (tap_ok ? diff : 0) * 4);
                 // channel order (see pl_row_pass "fix-up"): does a symbol chosen by an earlier channel disturb this one?
                 // The clamped band in symbols is [lo, lo + span]; a bin v lies in it iff ((v - lo) & 255) <= span.
-                const int lob = transp ? 0 : max(bl, 0), hib = transp ? 0 : min(bl + q, 255);
                 const int lo = lob - pred;
                 const unsigned span = (unsigned)(hib - lob);
                 const unsigned bf = min(bc, 0xfffff0u);
@@ -296,7 +304,7 @@ __device__ __forceinline__ unsigned pl_solo_chain(PlSoloSmem &sm, int f, int ch,
                     conflict |= earlier & inb & !same & near;
                     dup += (unsigned)(earlier & same);
                 }
-                const bool fails = act && !ok;
+                const bool fails = act && (!lutok || !tap_ok || (!single && !inr));
 #if PL_S_ONEVOTE
                 // one vote for the common case; the rare cases are told apart behind it
                 bool any_fail = false, any_conflict = false;
@@ -342,7 +350,7 @@ __device__ __forceinline__ unsigned pl_solo_chain(PlSoloSmem &sm, int f, int ch,
                         }
                         back = sym + pred;
                         ld = pl_solo_bin_load(bins_sh, bins3_sh, sym, three);
-                        diff = (transp || !act) ? 0 : want - sym;
+                        diff = (transp || !act) ? 0 : want - sym;   // (a replayed symbol lies in the band: within the table)
                         te = pl_lds32(tapc_sh + diff * 4);
                     }
                     pl_solo_commit(hk_sh, bm_sh, ld, sym, bc + 1u, rk << 7, actm, three);
