@@ -71,6 +71,7 @@ def parse_args():
                     help="K2 candidate choice: 1 bucket maxima, 0 scan only, -1 library default")
     ap.add_argument("--lean", type=int, default=-1, help="K2 large-batch kernel: 1/-1 on where it applies, 0 off")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-k4", action="store_true", help="skip the K4 (scanlines) roofline measurement")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows per core of the CPU sample (0 = auto)")
     a = ap.parse_args()
@@ -427,10 +428,19 @@ def main():
         ms_per_step = allmax(ms) / a.steps
     value = world * px_per_step_rank / (ms_per_step * 1e-3) / 1e6
 
+    # ---- K4 (filtered scanlines: the repo's one HBM-bound hot kernel), outside the timed region, on a batch of its
+    # own that is large enough to saturate HBM and small enough to sit next to nothing else ------------------------
+    k4 = None
+    if world == 1 and not a.no_k4:
+        batch.close()
+        batch = None
+        k4 = measure_k4(ctx, pngloss_b200, min(n, 296), w, h, a.strength, a.bleed)
+
     # ---- end to end through the host-buffer C-ABI calls -------------------------------------------------
     e2e = None
     if not a.no_e2e:
-        batch.close()                           # give the HBM back; the host-buffer calls allocate their own
+        if batch is not None:
+            batch.close()                       # give the HBM back; the host-buffer calls allocate their own
         batch = None
         if n == 1:
             e2e = e2e_single_image(a, ctx, pngloss_b200, host_img, seeds, w, h)
@@ -483,6 +493,15 @@ def main():
             # What bounds K2: every image is w*h dependent pixel steps per filter candidate;
             # a step costs `cycles_per_pixel_step` SM cycles of latency, and images * 5 such chains run at once.
             "latency_bound": latency_bound(info, n, w, h, k2_s, sm_mhz),
+            "roofline_k4": ({"bound": "hbm", "kernel": "pl_k4_scanlines", "achieved": k4["filter_gb_s"], "peak": peak,
+                             "unit": "GB/s", "frac": k4["filter_gb_s"] / peak, "traffic": None,
+                             "kernel_ms": k4["filter_ms"], "images": k4["images"],
+                             "algorithmic_bytes_per_px": 4 + k4["bytes_per_pixel"],
+                             "scan_kernel": {"kernel": "pl_k4_scan_output", "achieved": k4["scan_gb_s"],
+                                             "frac": k4["scan_gb_s"] / peak, "kernel_ms": k4["scan_ms"]},
+                             "note": "not part of the timed step: what the encoder's filtering pass costs on the "
+                                     "device (pngloss_b200_batch_scanlines), timed alone with CUDA events"}
+                            if k4 else None),
             "kernel_ms": {"k1_orig_hist": float(np.mean(k1_ms)), "k2_quantize": float(np.mean(k2_ms)),
                           "k3_batch_hist": float(np.mean(k3_ms))},
             "checks": {"symbols_counted": global_hist_sum,
@@ -499,6 +518,26 @@ def main():
         batch.close()
     ctx.barrier()
     ctx.close()
+
+
+def measure_k4(ctx, pngloss_b200, m, w, h, strength, bleed):
+    """Device time of the two scanline kernels on m quantised images (best of three)."""
+    batch = pngloss_b200.Batch(ctx, [w] * m, [h] * m, in_place=True)
+    for i in range(m):
+        batch.synth(i, 4 + i)
+    batch.run(strength, bleed)
+    batch.finish()
+    best = None
+    for _ in range(3):
+        batch.scanlines()
+        info = batch.scanline_info(0)
+        t = (info["k4_scan_ms"], info["k4_filter_ms"])
+        best = t if best is None else (min(best[0], t[0]), min(best[1], t[1]))
+    bpp = info["bytes_per_pixel"]
+    batch.close()
+    px = m * w * h
+    return {"images": m, "bytes_per_pixel": bpp, "scan_ms": best[0], "filter_ms": best[1],
+            "scan_gb_s": px * 4 / best[0] / 1e6, "filter_gb_s": (px * (4 + bpp) + m * h) / best[1] / 1e6}
 
 
 def latency_bound(info, n, w, h, k2_s, sm_mhz):
