@@ -37,6 +37,14 @@
 #ifndef PL_S_MIN_BLOCKS
 #define PL_S_MIN_BLOCKS(FPW) ((FPW) == 5 ? 2 : 1)   // FPW = 5: 128 registers, two CTAs (two images) per SM
 #endif
+// Who arrives on the ring's mbarriers: lane 0 on behalf of its warp, after a __syncwarp (the product), or every lane
+// itself (-DPL_S_ALL_ARRIVE=1: the sanitizer build - racecheck follows a thread's own arrive / wait only, and reports
+// the one-lane idiom as a race between the other lanes' accesses and the waiters'; profiles/r2_compute_sanitizer.txt).
+#ifndef PL_S_ALL_ARRIVE
+#define PL_S_ALL_ARRIVE 0
+#endif
+#define PL_S_ARRIVERS (PL_S_ALL_ARRIVE ? 32 : 1)
+#define PL_S_ARRIVES(lane) (PL_S_ALL_ARRIVE || (lane) == 0)
 #define PL_S_TAPC_HALF 512 // the chain's tap table covers differences -512 .. 511
 #define PL_S_BOFF 1024     // the band table covers here - predicted = -1024 .. 1023
 #define PL_S_HPAD 4        // entries between the candidates' histograms (bank stagger)
@@ -492,7 +500,7 @@ __device__ __forceinline__ unsigned pl_solo_chain(PlSoloSmem &sm, int f, int ch,
             __syncwarp();
         }
         // hand the tile to the post warps, the input slot back to the producer
-        if (lane == 0) {
+        if (PL_S_ARRIVES(lane)) {
             pl_mbar_arrive(&sm.out_full[s]);
             pl_mbar_arrive(&sm.pre_empty[s]);
         }
@@ -531,7 +539,7 @@ __device__ __forceinline__ void pl_solo_producer(PlSoloSmem &sm, int W, int y, i
         v.w = (o4 >> 24) | ((n4 >> 24) << 8) | ((unsigned)(unsigned short)e.w << 16);
         sm.pre[s][lane] = v;
         __syncwarp();
-        if (lane == 0) pl_mbar_arrive(&sm.pre_full[s]);
+        if (PL_S_ARRIVES(lane)) pl_mbar_arrive(&sm.pre_full[s]);
     }
 }
 
@@ -657,9 +665,9 @@ __device__ __forceinline__ void pl_solo_post(PlSoloSmem &sm, int pf, int chmask,
         }
         // give the previous tile back to the chain
         __syncwarp();
-        if (lane == 0 && t >= 1 && t - 1 < ntiles) pl_mbar_arrive(&sm.out_empty[(use + (unsigned)(t - 1)) % PL_S_STAGES]);
+        if (PL_S_ARRIVES(lane) && t >= 1 && t - 1 < ntiles) pl_mbar_arrive(&sm.out_empty[(use + (unsigned)(t - 1)) % PL_S_STAGES]);
     }
-    if (lane == 0 && ncell_tiles == ntiles) pl_mbar_arrive(&sm.out_empty[(use + (unsigned)(ntiles - 1)) % PL_S_STAGES]);
+    if (PL_S_ARRIVES(lane) && ncell_tiles == ntiles) pl_mbar_arrive(&sm.out_empty[(use + (unsigned)(ntiles - 1)) % PL_S_STAGES]);
 
 #pragma unroll
     for (int mk = 1; mk < 32; mk <<= 1) {
@@ -697,10 +705,10 @@ pl_k2_solo(const PlImageDev *imgs, const int *slots, int strength, int bleed, un
     if (tid == 0) {
         sm.img = imgs[idx];
         for (int s = 0; s < PL_S_STAGES; s++) {
-            pl_mbar_init(&sm.pre_full[s], 1);
-            pl_mbar_init(&sm.pre_empty[s], C::NCHAIN);
-            pl_mbar_init(&sm.out_full[s], C::NCHAIN);
-            pl_mbar_init(&sm.out_empty[s], PL_S_POSTW);
+            pl_mbar_init(&sm.pre_full[s], PL_S_ARRIVERS);
+            pl_mbar_init(&sm.pre_empty[s], C::NCHAIN * PL_S_ARRIVERS);
+            pl_mbar_init(&sm.out_full[s], C::NCHAIN * PL_S_ARRIVERS);
+            pl_mbar_init(&sm.out_empty[s], PL_S_POSTW * PL_S_ARRIVERS);
         }
         pl_fence_mbar_init();
     }
