@@ -1205,18 +1205,20 @@ __device__ __forceinline__ int pl_k4_row_type(const PlScanDev &im, int y, int ro
 }
 
 // Vector path of K4 (width a multiple of 4, so rows are 16-byte aligned): the CTA's rows are cut into
-// segments of 256 * PL_K4_PX pixels; a thread takes PL_K4_GROUPS groups of four pixels of a segment, each
-// 4 * bpp bytes = bpp whole words of the output stream, which are staged as words; the copy-out realigns the stream to the destination with funnel
+// segments of 256 * PL_K4_PX pixels; a thread takes PL_K4_GROUPS groups of four pixels of a segment - group k of
+// thread t is group k * 256 + t of the segment, so that the loads of a warp are contiguous and its 16-byte stage
+// stores hit every bank once - each 4 * bpp bytes = bpp whole words of the output stream, which are staged as words;
+// the copy-out realigns the stream to the destination with funnel
 // shifts and writes 16-byte vectors.  The loads of segment s + 1 are issued before segment s is copied out and
 // the stage is double buffered, so there is one barrier per segment and loads are always in flight.
 #ifndef PL_K4_GROUPS
-#define PL_K4_GROUPS 2   /* 4-pixel groups per thread and segment (measured: profiles/r2_k4.txt) */
+#define PL_K4_GROUPS 4   /* 4-pixel groups per thread and segment (measured: profiles/r2_k4.txt) */
 #endif
 #define PL_K4_PX (4 * PL_K4_GROUPS)
 #define PL_K4_STAGE_WORDS (PL_K4_THREADS * PL_K4_PX + 8)
 struct PlK4Seg {
-    uint4 c4[PL_K4_GROUPS], u4[PL_K4_GROUPS];   // the thread's pixels of the row and of the row above
-    unsigned left, ul;                          // the pixel before them, narrowed
+    uint4 c4[PL_K4_GROUPS], u4[PL_K4_GROUPS];   // the thread's groups of four pixels of the row and of the row above
+    unsigned left[PL_K4_GROUPS], ul[PL_K4_GROUPS];   // the pixel before each group, narrowed
 };
 // four pixels' worth of filtered bytes: the filter type is the same for the whole CTA, so the switch is uniform
 template <int BPP, int TYPE>
@@ -1238,22 +1240,20 @@ __device__ __forceinline__ void pl_k4_vector_rows(const PlScanDev &im, int first
     const size_t stride = 1 + (size_t)W * BPP;
     const int seg_px = PL_K4_THREADS * PL_K4_PX;
     auto load = [&](int y, int x0, PlK4Seg &g) {
-        const int x = x0 + tid * PL_K4_PX;
-        if (y < H && x < W) {
-            const uchar4 *row = im.px + (size_t)y * W;
-            // (the width is a multiple of 4, so a thread's 4-pixel groups are either whole or beyond the row)
+        const uchar4 *row = im.px + (size_t)y * W;
 #pragma unroll
-            for (int k = 0; k < PL_K4_GROUPS; k++)
-                g.c4[k] = x + 4 * k < W ? *(const uint4 *)(row + x + 4 * k) : make_uint4(0u, 0u, 0u, 0u);
-            g.left = x ? pl_k4_narrow(pl_u32(row[x - 1]), BPP) : 0u;
-            g.ul = 0u;
-#pragma unroll
-            for (int k = 0; k < PL_K4_GROUPS; k++) g.u4[k] = make_uint4(0u, 0u, 0u, 0u);
-            if (y) {
-#pragma unroll
-                for (int k = 0; k < PL_K4_GROUPS; k++)
-                    if (x + 4 * k < W) g.u4[k] = *(const uint4 *)(row - W + x + 4 * k);
-                g.ul = x ? pl_k4_narrow(pl_u32(row[x - 1 - W]), BPP) : 0u;
+        for (int k = 0; k < PL_K4_GROUPS; k++) {
+            const int x = x0 + (k * PL_K4_THREADS + tid) * 4;
+            // (the width is a multiple of 4, so a group is either whole or beyond the row)
+            g.c4[k] = g.u4[k] = make_uint4(0u, 0u, 0u, 0u);
+            g.left[k] = g.ul[k] = 0u;
+            if (y < H && x < W) {
+                g.c4[k] = *(const uint4 *)(row + x);
+                if (x) g.left[k] = pl_k4_narrow(pl_u32(row[x - 1]), BPP);
+                if (y) {
+                    g.u4[k] = *(const uint4 *)(row - W + x);
+                    if (x) g.ul[k] = pl_k4_narrow(pl_u32(row[x - 1 - W]), BPP);
+                }
             }
         }
     };
@@ -1266,10 +1266,11 @@ __device__ __forceinline__ void pl_k4_vector_rows(const PlScanDev &im, int first
         unsigned *stage_w = stage[buf];
         unsigned char *dst_row = im.scan + (size_t)y * stride;
         if (x0 == 0 && tid == 0) dst_row[0] = (unsigned char)type;
-        unsigned left = seg.left, ul = seg.ul;
 #pragma unroll
         for (int k = 0; k < PL_K4_GROUPS; k++) {
-            if (tid * PL_K4_PX + 4 * k < npx) {
+            const int grp = k * PL_K4_THREADS + tid;   // group of four pixels within the segment
+            if (grp * 4 < npx) {
+                unsigned left = seg.left[k], ul = seg.ul[k];
                 unsigned r[4];
                 switch (type) {
                 case 0: pl_k4_filter4<BPP, 0>(seg.c4[k], seg.u4[k], left, ul, r); break;
@@ -1278,7 +1279,7 @@ __device__ __forceinline__ void pl_k4_vector_rows(const PlScanDev &im, int first
                 case 3: pl_k4_filter4<BPP, 3>(seg.c4[k], seg.u4[k], left, ul, r); break;
                 default: pl_k4_filter4<BPP, 4>(seg.c4[k], seg.u4[k], left, ul, r); break;
                 }
-                unsigned *sp = stage_w + (tid * PL_K4_GROUPS + k) * BPP;
+                unsigned *sp = stage_w + grp * BPP;
                 if (BPP == 4) {
                     *(uint4 *)sp = make_uint4(r[0], r[1], r[2], r[3]);
                 } else if (BPP == 3) {
@@ -1309,11 +1310,23 @@ __device__ __forceinline__ void pl_k4_vector_rows(const PlScanDev &im, int first
         const int nvec = (mis + len + 15) >> 4;
         const int sh = ((16 - mis) & 3) * 8;                        // stream word -> destination word shift
         const unsigned char *sb = (const unsigned char *)stage_w;
+        // The five stream words a vector needs, stage_w[4 vi - c .. 4 vi - c + 4] with c = ceil(mis / 4), lie in the
+        // aligned quads vi - 1 and vi: two conflict-free 16-byte reads (five 4-byte reads at a four-word stride between
+        // threads cost four bank-conflict passes each; profiles/r2_k4.txt).
+        const int c = (mis + 3) >> 2;
+        const uint4 *sq = (const uint4 *)stage_w;
         for (int vi = tid; vi < nvec; vi += PL_K4_THREADS) {
             const int o = vi * 16 - mis;                            // stream offset of the vector's first byte
             if (o >= 0 && o + 16 <= len) {
-                const unsigned *q = stage_w + (o >> 2);
-                const unsigned w0 = q[0], w1 = q[1], w2 = q[2], w3 = q[3], w4 = q[4];
+                const uint4 pq = vi ? sq[vi - 1] : make_uint4(0u, 0u, 0u, 0u), cq = sq[vi];
+                unsigned w0, w1, w2, w3, w4;
+                switch (c) {   // CTA-uniform
+                case 0: w0 = cq.x; w1 = cq.y; w2 = cq.z; w3 = cq.w; w4 = 0u; break;   // (aligned: no shift, w4 unused)
+                case 1: w0 = pq.w; w1 = cq.x; w2 = cq.y; w3 = cq.z; w4 = cq.w; break;
+                case 2: w0 = pq.z; w1 = pq.w; w2 = cq.x; w3 = cq.y; w4 = cq.z; break;
+                case 3: w0 = pq.y; w1 = pq.z; w2 = pq.w; w3 = cq.x; w4 = cq.y; break;
+                default: w0 = pq.x; w1 = pq.y; w2 = pq.z; w3 = pq.w; w4 = cq.x; break;
+                }
                 *(uint4 *)(g0 + o) = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh),
                                                 __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
             }
