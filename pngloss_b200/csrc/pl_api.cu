@@ -550,7 +550,8 @@ static int use_solo(const pngloss_b200_batch *b, unsigned strength) {
     const pngloss_b200_ctx *ctx = b->ctx;
     uint32_t wmax = 0;
     for (size_t i = 0; i < b->n; i++) wmax = std::max(wmax, b->w[i]);
-    const bool table = strength + 1 >= PL_BM_MIN_STEP && strength + 1 <= PL_BM_MAX_STEP && wmax < PL_BM_MAX_WIDTH;
+    // (its tables have room for the one-symbol buckets of the smallest strengths, unlike the other kernels')
+    const bool table = strength + 1 <= PL_BM_MAX_STEP && wmax < PL_BM_MAX_WIDTH;
     if (!table || ctx->solo == 0) return 0;
     if (ctx->solo > 0) return (ctx->lpc == 0 || ctx->lpc == 8) ? (ctx->solo == 2 ? 1 : 5) : 0;
     const size_t sms = ctx->sm_count > 0 ? (size_t)ctx->sm_count : 148;

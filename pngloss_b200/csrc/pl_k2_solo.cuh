@@ -48,7 +48,7 @@
 #define PL_S_TAPC_HALF 512 // the chain's tap table covers differences -512 .. 511
 #define PL_S_BOFF 1024     // the band table covers here - predicted = -1024 .. 1023
 #define PL_S_HPAD 4        // entries between the candidates' histograms (bank stagger)
-#define PL_S_BM_ROW (PL_BM_MAX + 2)
+#define PL_S_BM_ROW 264     // entries of a candidate's bucket table: up to 129 + 130 buckets (strength 0) + Z+
 #define PL_S_POSTW PL_FILTERS
 
 // Warp roles.  The hardware arbiter prefers the higher warp id of a sub-partition (warp id % 4), so a chain warp is the
@@ -75,6 +75,19 @@ struct PlSoloCfg {
     __device__ static int chain_index(int w) { return FPW == 5 ? 0 : w - 7; }
 };
 
+// Buckets of this kernel: pl_bm_counts without its lower strength limit (that one comes from the 18-entry tables of
+// pl_k2_quantize / pl_k2_lean; here a candidate's table has room for the 259 one-symbol buckets of strength 0).
+__device__ __forceinline__ PlBm pl_solo_bm_counts(int step, int width) {
+    PlBm b;
+    const bool on = step >= 1 && step <= PL_BM_MAX_STEP && width < PL_BM_MAX_WIDTH;
+    const int KP = 128 / step, KN = 129 / step;
+    b.P1 = on ? KP + 1 : 0;
+    b.N1 = on ? KN + 1 : 0;
+    b.seam_p = on ? 256 - KN * step - (step - 1) : 999;
+    b.seam_n = on ? KP * step + (step - 1) - 256 : -999;
+    return b;
+}
+
 struct PlSoloSmem {
     // per candidate and symbol: high word = running symbol_frequency, low word = rank of
     // original_frequency[filter][symbol] << PL_KEY_RANK_SHIFT (the two halves of K2's candidate key)
@@ -83,7 +96,7 @@ struct PlSoloSmem {
     uint32_t base[256];                     // symbol_frequency at the start of the row
     uint4 bins[256];                        // the table entries of a histogram bin: {entry 0, its base, entry 1, its base}
     uint2 bins3[256];                       // ... and a third one (large strengths only)
-    uint32_t band[2 * PL_S_BOFF];           // here - predicted -> band start << 16 | entry if 0 <= predicted <= 255 << 8 | entry
+    uint32_t band[2 * PL_S_BOFF];           // here - predicted -> band start << 16 | zero-band flag | entry (pl_solo_band_entry)
     uint32_t tapc[2 * PL_S_TAPC_HALF];      // chain: difference -> the two taps that stay in the row (rem | threes << 16)
     uint32_t dl32[2 * PL_DL32_HALF];        // post warps: all five taps (pl_pack_taps6)
     uint4 pre[PL_S_STAGES][PL_S_T + 1];     // per pixel, word ch: orig | above << 8 | incoming error << 16
@@ -134,8 +147,8 @@ __device__ __forceinline__ PlBinEntries pl_solo_bin_entries(const PlSoloSmem &sm
 }
 
 // The band of admissible symbols of a byte whose here - predicted is `want` (reference src/optimize_state.c:186-193)
-// and the table entry that holds its winner: band start << 16 | entry if symbol 0 is admissible << 8 | entry
-// otherwise (0xff: no entry).  The two differ for the band [-q, 0] only (Z+ against negative bucket 0).
+// and the table entry that holds its winner: band start << 16 | 0x8000 if the band is [-q, 0] (Z+ instead of negative
+// bucket 0 when symbol 0 is admissible) | entry (0x7ff: none).
 __device__ __forceinline__ unsigned pl_solo_band_entry(const PlBm &bmc, int want, int q, int step, unsigned step_magic) {
     const bool neg = want < 0;
     const unsigned m = (unsigned)(neg ? -want : want);
@@ -143,9 +156,9 @@ __device__ __forceinline__ unsigned pl_solo_band_entry(const PlBm &bmc, int want
     const int ks = (int)kq * step;
     const int lo_u = neg ? -(ks + q) : ks;
     const bool tvalid = kq < (unsigned)(neg ? bmc.N1 : bmc.P1);
-    const unsigned t = tvalid ? kq + (neg ? (unsigned)bmc.P1 : 0u) : 0xffu;
-    const unsigned tz = (tvalid && neg && kq == 0u) ? (unsigned)(bmc.P1 + bmc.N1) : t;
-    return ((unsigned)lo_u << 16) | (tz << 8) | t;
+    const unsigned t = tvalid ? kq + (neg ? (unsigned)bmc.P1 : 0u) : 0x7ffu;
+    const unsigned z = (tvalid && neg && kq == 0u) ? 0x8000u : 0u;
+    return ((unsigned)lo_u << 16) | z | t;
 }
 
 // Commit of a byte: count the symbol, and let its new key (count `now`, rank) enter every table entry that holds its
@@ -213,7 +226,7 @@ __device__ __forceinline__ unsigned pl_solo_chain(PlSoloSmem &sm, int f, int ch,
     // predictor of this lane's candidate, branch-free (FPW = 5: the lanes of a warp differ)
     const int ma = (ff == 2 || ff == 3) ? 255 : 0, ml = (ff == 1 || ff == 3) ? 255 : 0, sh = ff == 3 ? 1 : 0;
     const unsigned pm = ff == 4 ? ~0u : 0u;
-    const PlBm bmc = pl_bm_counts(step, W);
+    const PlBm bmc = pl_solo_bm_counts(step, W);
     const int P1 = bmc.P1, N1 = bmc.N1, tz = bmc.P1 + bmc.N1;
     const bool table = try_fast && P1 > 0;
     const bool al = alpha_rule && ch == 3;
@@ -264,9 +277,9 @@ __device__ __forceinline__ unsigned pl_solo_chain(PlSoloSmem &sm, int f, int ch,
                 // ================================ FAST path ================================
                 const unsigned bw = pl_lds32(band_sh + (((unsigned)(want + PL_S_BOFF)) & (2u * PL_S_BOFF - 1u)) * 4u);
                 const unsigned long long xe64 = pl_lds64(hk_sh + ((unsigned)ex0 & 255u) * 8u);
-                const unsigned t8 = (((unsigned)pred <= 255u) ? (bw >> 8) : bw) & 255u;
+                const unsigned t8 = ((bw & 0x8000u) && (unsigned)pred <= 255u) ? (unsigned)tz : (bw & 0x7ffu);
                 const unsigned long long be64 = pl_lds64(bm_sh + t8 * 8u);
-                const bool lutok = (unsigned)(want + PL_S_BOFF) < 2u * PL_S_BOFF, tv = t8 != 255u;
+                const bool lutok = (unsigned)(want + PL_S_BOFF) < 2u * PL_S_BOFF, tv = t8 != 0x7ffu;
                 const int bl = ((int)bw >> 16) + pred;          // the band in byte values: [bl, bl + q]
                 const unsigned be_x = (unsigned)be64, base_l = (unsigned)(be64 >> 32);
                 const int wbyte = bl + 127 - (int)(be_x & 127u);
@@ -770,7 +783,7 @@ pl_k2_solo(const PlImageDev *imgs, const int *slots, int strength, int bleed, un
         for (;;) {
             const int step = q + 1;
             const unsigned step_magic = pl_make_magic((unsigned)step);
-            const PlBm bmc = pl_bm_counts(step, W);
+            const PlBm bmc = pl_solo_bm_counts(step, W);
             // ---- tables of the pass.  Bucket winners of every candidate at the start of the row (all candidates hold
             // the same counts, the tie-break rank differs), see pl_lean_row_pass; entry tz ("Z+") is the whole zero
             // band [-q, 0], negative bucket 0 is [-q, -1] ---------------------------------------------------------------

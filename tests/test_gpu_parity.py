@@ -669,14 +669,14 @@ def test_lean_kernel_4k_golden_24_images(ctx, oracle):
 @pytest.mark.parametrize("solo", [1, 2], ids=["one-chain-warp", "five-chain-warps"])
 def test_solo_kernel_golden_and_random(ctx, oracle, solo):
     """The latency kernel (pl_k2_solo: one image per CTA, chain / producer / post warps, fast path + general path)
-    against the reference's goldens - every small and medium vector whose strength has a winner table, through the
+    against the reference's goldens - every small and medium vector of strength 0 .. 126, through the
     drop-in entry and in batches - and against the oracle on random images of every mode (noise, transparent
     holes, few grey levels, dark and bright: the clamped bands and the channel replay)."""
     ctx.set_lanes(8)
     ctx.set_solo(solo)
     ran = 0
     for c in cases("small", "medium"):
-        if not 15 <= c["strength"] <= 126:
+        if c["strength"] > 126:
             continue
         img = load_input(c, oracle).copy()
         rf = np.zeros(img.shape[0], np.uint8) if c["filters"] else None
@@ -689,7 +689,7 @@ def test_solo_kernel_golden_and_random(ctx, oracle, solo):
     assert ran >= 20
     rng = np.random.default_rng(199)
     for (w, h, s, b) in [(64, 40, 20, 2), (101, 17, 19, 1), (37, 33, 63, 3), (260, 9, 126, 2), (48, 12, 15, 2),
-                         (300, 20, 85, 2), (31, 50, 40, 1)]:
+                         (300, 20, 85, 2), (31, 50, 40, 1), (90, 12, 0, 2), (64, 16, 3, 1), (75, 10, 14, 2)]:
         n = 10
         imgs = []
         for i in range(n):
@@ -738,7 +738,7 @@ def test_solo_kernel_suite_images(ctx, oracle, solo):
     """The eight full suite images (tier "suite" goldens of the unmodified reference) through the latency kernel."""
     ctx.set_lanes(8)
     ctx.set_solo(solo)
-    cs = [c for c in cases("suite") if 15 <= c["strength"] <= 126]
+    cs = [c for c in cases("suite") if c["strength"] <= 126]
     assert cs
     for c in cs:
         img = load_input(c, oracle).copy()

@@ -374,3 +374,21 @@ def test_emu_solo_noise_ties_and_paths(emu, oracle, flag):
     wide = (np.random.default_rng(99).integers(0, 6, (2, 256, 4)) * 51).astype(np.uint8)
     for s in (126, 120, 100):
         compare(emu, oracle, [wide], s, 2, False, flag)
+
+
+@pytest.mark.parametrize("flag", [SOLO5, SOLO1])
+def test_emu_solo_small_strengths(emu, oracle, flag):
+    """Strengths below 15: the other kernels have no winner table there; the latency kernel's has room for up to 259
+    buckets per candidate (one symbol each at strength 0), so its fast path covers them too."""
+    before = emu.counters()
+    rng = np.random.default_rng(31)
+    noise = rng.integers(0, 256, (5, 40, 4), dtype=np.uint8)
+    holes = noise.copy()
+    holes[rng.random((5, 40)) < 0.3, 3] = 0
+    few = (rng.integers(0, 4, (5, 40, 4)) * 85).astype(np.uint8)
+    edge = np.concatenate([rng.integers(0, 12, (5, 20, 4)), 255 - rng.integers(0, 12, (5, 20, 4))], axis=1).astype(np.uint8)
+    imgs = [noise, holes, few, edge, oracle.synth(40, 5, 9), to_bpp(noise, 1), to_bpp(holes, 2), to_bpp(edge, 3)]
+    for s, b, nf in ((0, 2, False), (1, 1, False), (2, 2, True), (7, 3, False), (14, 2, False)):
+        compare(emu, oracle, imgs, s, b, nf, flag)
+    after = emu.counters()
+    assert after["solo_fast"] > before["solo_fast"]
