@@ -298,8 +298,9 @@ __device__ __forceinline__ unsigned pl_solo_chain(PlSoloSmem &sm, int f, int ch,
                 const bool e_wins = fe && ce >= base_l && ke >= kw;
                 back = single ? lob : e_wins ? o : wbyte;
                 int sym = back - pred;
-                unsigned bc = single ? (unsigned)(fx64 >> 32) : e_wins ? ce : base_l + (be_x >> PL_BM_COUNT_SHIFT);
-                unsigned rk = single ? (unsigned)fx64 >> PL_KEY_RANK_SHIFT : e_wins ? re : (kw & 255u);
+                // (the forced symbol's count and rank arrive late - their load needed the band - and are kept off the
+                // chain: they are only used behind the vote)
+                const unsigned bc_ns = e_wins ? ce : base_l + (be_x >> PL_BM_COUNT_SHIFT);
                 // what the commit needs from the tables, for the provisional symbol (it is final unless the channel order
                 // is replayed below): issued here, the loads are back by the time the vote is
                 PlBinLoaded ld = pl_solo_bin_load(bins_sh, bins3_sh, sym, three);
@@ -310,7 +311,10 @@ __device__ __forceinline__ unsigned pl_solo_chain(PlSoloSmem &sm, int f, int ch,
                 // The clamped band in symbols is [lo, lo + span]; a bin v lies in it iff ((v - lo) & 255) <= span.
                 const int lo = lob - pred;
                 const unsigned span = (unsigned)(hib - lob);
-                const unsigned bf = min(bc, 0xfffff0u);
+                // What the other channels see of this one: its symbol and its count.  A one-value band publishes the
+                // largest count instead of its own (late) one: that can only make a later channel's test more
+                // conservative, and this lane's own test cannot fire (a symbol inside a one-value band is the same symbol).
+                const unsigned bf = single ? 0xfffff0u : min(bc_ns, 0xfffff0u);
                 const unsigned mine = (bf << 8) | ((unsigned)sym & 255u);
                 const unsigned mhi = mine & ~255u, nlo24 = (unsigned)(-lo) << 24, span24 = span << 24;
                 bool conflict = false;
@@ -339,6 +343,8 @@ __device__ __forceinline__ unsigned pl_solo_chain(PlSoloSmem &sm, int f, int ch,
 #endif
                 if (!any_fail) {
                     PL_EMU_COUNT(PL_CNT_SOLO_FAST);
+                    unsigned bc = single ? (unsigned)(fx64 >> 32) : bc_ns;
+                    unsigned rk = single ? (unsigned)fx64 >> PL_KEY_RANK_SHIFT : e_wins ? re : (kw & 255u);
                     if (!any_conflict) {
                         bc += dup;   // every provisional winner is final; mine has been counted dup times since the look-up
                     } else {
