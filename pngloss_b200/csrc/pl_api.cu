@@ -544,7 +544,7 @@ static int choose_lpc(const pngloss_b200_batch *b) {
 
 // The latency kernel (pl_k2_solo.cuh: 3.0 against 2.0 Mpx/s per image, profiles/r2_sweep_solo.txt) takes a batch when
 // every image can have a CTA of its own with at most two CTAs per SM (its 123 registers x 256 threads allow two), and
-// the strength has a winner table.  0 = no, 5 / 1 = filter candidates per chain warp.  An explicit lane mapping
+// the strength is at most 126 (where its winner tables exist).  0 = no, 5 / 1 = filter candidates per chain warp.  An explicit lane mapping
 // (pngloss_b200_ctx_set_lanes) keeps the generic kernel unless the latency kernel is asked for explicitly.
 static int use_solo(const pngloss_b200_batch *b, unsigned strength) {
     const pngloss_b200_ctx *ctx = b->ctx;
