@@ -89,9 +89,9 @@ int pngloss_b200_ctx_set_lean(pngloss_b200_ctx *ctx, int mode);
 /* Kernel variant for batches small enough that every image gets a CTA (and an SM) of its own - a single image above
  * all, the reference's one-file-per-call use (src/pngloss.c:173-205,266): the latency kernel (warp-specialised: chain /
  * producer / post warps) for strengths up to 126.  -1 (default) = for batches of at
- * most two images per SM, unless a lane mapping was set explicitly; 1 = one chain warp for the five filter candidates,
- * 2 = one chain warp per candidate (both: whenever the lane mapping is 0 or 8); 0 = never.  A tuning knob, results
- * never depend on it. */
+ * most four images per SM, unless a lane mapping was set explicitly; 1 = one chain warp for the five filter candidates
+ * in a CTA of eight warps, 2 = one chain warp per candidate, 3 = one chain warp in a CTA of four warps (1 .. 3:
+ * whenever the lane mapping is 0 or 8); 0 = never.  A tuning knob, results never depend on it. */
 int pngloss_b200_ctx_set_solo(pngloss_b200_ctx *ctx, int mode);
 /* CUDA-event stopwatch on the context's stream (what bench.py times with). */
 int pngloss_b200_ctx_timer_start(pngloss_b200_ctx *ctx);

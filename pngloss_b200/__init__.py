@@ -255,8 +255,8 @@ class Context:
         self._check(self.lib.pngloss_b200_ctx_set_lean(self.handle, mode))
 
     def set_solo(self, mode: int):
-        """The latency kernel for one-image-per-CTA grids: 1 one chain warp, 2 five chain warps, -1 library's choice,
-        0 never."""
+        """The latency kernel for one-image-per-CTA grids: 1 one chain warp (eight warps per CTA), 2 five chain warps,
+        3 one chain warp in a four-warp CTA (up to four CTAs per SM), -1 library's choice, 0 never."""
         self._check(self.lib.pngloss_b200_ctx_set_solo(self.handle, mode))
 
     # ---- multi-GPU: the library's own NCCL communicator (pl_comm.cuh) --------------------------------------

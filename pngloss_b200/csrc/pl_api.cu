@@ -184,7 +184,7 @@ extern "C" int pngloss_b200_ctx_set_lean(pngloss_b200_ctx *ctx, int mode) {
 }
 
 extern "C" int pngloss_b200_ctx_set_solo(pngloss_b200_ctx *ctx, int mode) {
-    if (!ctx || mode < -1 || mode > 2) return PNGLOSS_B200_INVALID_ARGUMENT;
+    if (!ctx || mode < -1 || mode > 3) return PNGLOSS_B200_INVALID_ARGUMENT;
     ctx->solo = mode;
     return PNGLOSS_B200_SUCCESS;
 }
@@ -511,12 +511,14 @@ static int launch_k2_lean(pngloss_b200_batch *b, int nblocks, unsigned strength,
 }
 
 // the latency kernel: one image per CTA, chain / producer / post warps (pl_k2_solo.cuh)
-template <int FPW>
+template <int FPW, bool COMPACT>
 static int launch_k2_solo(pngloss_b200_batch *b, int nblocks, unsigned strength, long bleed) {
     pngloss_b200_ctx *ctx = b->ctx;
     const size_t smem = sizeof(PlSoloSmem) + 16;
-    PL_CUDA(ctx, cudaFuncSetAttribute(pl_k2_solo<FPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pl_k2_solo<FPW><<<nblocks, PlSoloCfg<FPW>::THREADS, smem, b->stream>>>(
+    PL_CUDA(ctx, cudaFuncSetAttribute(pl_k2_solo<FPW, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PL_CUDA(ctx, cudaFuncSetAttribute(pl_k2_solo<FPW, COMPACT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+    pl_k2_solo<FPW, COMPACT><<<nblocks, PlSoloCfg<FPW, COMPACT>::THREADS, smem, b->stream>>>(
         b->dimgs, b->dslots, (int)strength, (int)bleed, (unsigned)(ctx->sm_count > 0 ? ctx->sm_count : 148));
     PL_CUDA(ctx, cudaGetLastError());
     b->info[0] = (uint32_t)nblocks;
@@ -543,9 +545,13 @@ static int choose_lpc(const pngloss_b200_batch *b) {
 }
 
 // The latency kernel (pl_k2_solo.cuh: 3.0 against 2.0 Mpx/s per image, profiles/r2_sweep_solo.txt) takes a batch when
-// every image can have a CTA of its own with at most two CTAs per SM (its 123 registers x 256 threads allow two), and
+// every image can have a CTA of its own with at most four CTAs per SM (eight-warp CTAs up to two per SM, four-warp
+// CTAs beyond: 592 images run at 1224 Mpx/s against 883 for the generic kernel at two lanes per channel), and
 // the strength is at most 126 (where its winner tables exist).  0 = no, 5 / 1 = filter candidates per chain warp.  An explicit lane mapping
 // (pngloss_b200_ctx_set_lanes) keeps the generic kernel unless the latency kernel is asked for explicitly.
+#ifndef PL_SOLO_MAX_CTAS_PER_SM
+#define PL_SOLO_MAX_CTAS_PER_SM 4   /* four-warp CTAs: 122 registers x 128 threads, 55 KB of shared memory */
+#endif
 static int use_solo(const pngloss_b200_batch *b, unsigned strength) {
     const pngloss_b200_ctx *ctx = b->ctx;
     uint32_t wmax = 0;
@@ -555,7 +561,7 @@ static int use_solo(const pngloss_b200_batch *b, unsigned strength) {
     if (!table || ctx->solo == 0) return 0;
     if (ctx->solo > 0) return (ctx->lpc == 0 || ctx->lpc == 8) ? (ctx->solo == 2 ? 1 : 5) : 0;
     const size_t sms = ctx->sm_count > 0 ? (size_t)ctx->sm_count : 148;
-    return (ctx->lpc == 0 && b->n <= 2 * sms) ? 5 : 0;
+    return (ctx->lpc == 0 && b->n <= PL_SOLO_MAX_CTAS_PER_SM * sms) ? 5 : 0;
 }
 
 // Host-side part of a run: CTA packing, descriptors and the cleared accumulators, enqueued on `stream`
@@ -636,7 +642,11 @@ static int launch_run(pngloss_b200_batch *b, unsigned strength, long bleed, int 
                       (ctx->lean > 0 || (ctx->lean < 0 && nblocks > 2 * (ctx->sm_count > 0 ? ctx->sm_count : 148)));
     const int solo = lpc == 8 ? use_solo(b, strength) : 0;
     int rc;
-    if (solo) rc = solo == 5 ? launch_k2_solo<5>(b, nblocks, strength, bleed) : launch_k2_solo<1>(b, nblocks, strength, bleed);
+    // (one chain warp: eight warps per CTA up to two CTAs per SM, the four-warp layout beyond)
+    const bool compact = ctx->solo == 3 || (ctx->solo < 0 && nblocks > 2 * (ctx->sm_count > 0 ? ctx->sm_count : 148));
+    if (solo) rc = solo == 1 ? launch_k2_solo<1, false>(b, nblocks, strength, bleed)
+                   : compact ? launch_k2_solo<5, true>(b, nblocks, strength, bleed)
+                             : launch_k2_solo<5, false>(b, nblocks, strength, bleed);
     else if (lean) rc = launch_k2_lean(b, nblocks, strength, bleed);
     else
     switch (lpc) {

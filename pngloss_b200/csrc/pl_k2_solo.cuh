@@ -34,9 +34,6 @@
 #ifndef PL_S_ONEVOTE
 #define PL_S_ONEVOTE 0     // measured (profiles/r2_solo_variants.txt)
 #endif
-#ifndef PL_S_MIN_BLOCKS
-#define PL_S_MIN_BLOCKS(FPW) ((FPW) == 5 ? 2 : 1)   // FPW = 5: 128 registers, two CTAs (two images) per SM
-#endif
 // Who arrives on the ring's mbarriers: lane 0 on behalf of its warp, after a __syncwarp (the product), or every lane
 // itself (-DPL_S_ALL_ARRIVE=1: the sanitizer build - racecheck follows a thread's own arrive / wait only, and reports
 // the one-lane idiom as a race between the other lanes' accesses and the waiters'; profiles/r2_compute_sanitizer.txt).
@@ -49,21 +46,30 @@
 #define PL_S_BOFF 1024     // the band table covers here - predicted = -1024 .. 1023
 #define PL_S_HPAD 4        // entries between the candidates' histograms (bank stagger)
 #define PL_S_BM_ROW 264     // entries of a candidate's bucket table: up to 129 + 130 buckets (strength 0) + Z+
-#define PL_S_POSTW PL_FILTERS
 
 // Warp roles.  The hardware arbiter prefers the higher warp id of a sub-partition (warp id % 4), so a chain warp is the
-// higher warp of its sub-partition.  FPW = 5 (8 warps): the chain warp is warp 4 + r and warp r idles at the CTA
-// barriers, so that the chain has the scheduler of sub-partition r to itself; r rotates with the CTA index (wave
-// number), so that the chain warps of the CTAs that share an SM sit on different schedulers.  The other six warps
-// are, in ascending order, the producer and the five post warps.  FPW = 1 (12 warps): warps 0 producer, 1 .. 5 post,
-// 6 idle, 7 .. 11 chain.
-template <int FPW>
+// higher warp of its sub-partition.
+//   FPW = 5 (8 warps, up to two CTAs per SM): the chain warp is warp 4 + r and warp r idles at the CTA barriers, so that
+//     the chain has the scheduler of sub-partition r to itself; r rotates with the CTA index (wave number), so that the
+//     chain warps of the CTAs that share an SM sit on different schedulers.  The other six warps are, in ascending
+//     order, the producer and the five post warps.
+//   FPW = 5, compact (4 warps, up to four CTAs per SM - batches of 297 .. 592 images): warp r is the chain warp, the
+//     other three are the producer and two post warps (candidates 0 2 4 and 1 3).
+//   FPW = 1 (12 warps): warps 0 producer, 1 .. 5 post, 6 idle, 7 .. 11 chain.
+template <int FPW, bool COMPACT = false>
 struct PlSoloCfg {
     static const int NCHAIN = PL_FILTERS / FPW;             // chain warps
-    static const int NWARPS = FPW == 5 ? 8 : 12;
+    static const int NWARPS = FPW == 5 ? (COMPACT ? 4 : 8) : 12;
     static const int THREADS = 32 * NWARPS;
-    // role of warp w: -3 idle, -2 chain, -1 producer, 0 .. 4 post warp of that candidate
+    static const int NPOSTW = COMPACT ? 2 : PL_FILTERS;     // post warps
+    static const int NF = COMPACT ? 3 : 1;                  // candidates per post warp (at most)
+    static const int MIN_BLOCKS = FPW == 5 ? (COMPACT ? 4 : 2) : 1;
+    // role of warp w: -3 idle, -2 chain, -1 producer, 0 .. post warp index
     __device__ static int role(int w, int rot) {
+        if (FPW == 5 && COMPACT) {
+            if (w == rot) return -2;
+            return w - (w > rot ? 1 : 0) - 1;               // the other three, ascending: -1, 0, 1
+        }
         if (FPW == 5) {
             if (w == 4 + rot) return -2;
             if (w == rot) return -3;
@@ -562,9 +568,15 @@ __device__ __forceinline__ void pl_solo_producer(PlSoloSmem &sm, int W, int y, i
     }
 }
 
-// ---- post warp of candidate pf: one lane per error cell / pixel -----------------------------------------------------
-__device__ __forceinline__ void pl_solo_post(PlSoloSmem &sm, int pf, int chmask, int W, int y, int parity,
-                                             int prev_w, bool adaptive, unsigned bleed_magic, unsigned use) {
+// ---- post warps: one lane per error cell / pixel ---------------------------------------------------------------------
+struct PlPostAcc {
+    unsigned long long derr;
+    unsigned as0, as1, as2, as3, as4;
+};
+// cells / pixels t * 32 .. t * 32 + 31 of candidate pf
+__device__ __forceinline__ void pl_solo_post_tile(PlSoloSmem &sm, int pf, int t, int chmask, int W, int y, int parity,
+                                                  int prev_w, bool adaptive, unsigned bleed_magic, unsigned use,
+                                                  PlPostAcc &acc) {
     const int lane = threadIdx.x & 31;
     const PlImageDev &im = sm.img;
     const int EW = W + PL_ERR_PAD;
@@ -577,110 +589,125 @@ __device__ __forceinline__ void pl_solo_post(PlSoloSmem &sm, int pf, int chmask,
     const uchar4 *rin_up = im.oprev;
     const uchar4 *rout_up = im.out + (size_t)(y ? y - 1 : 0) * W;
     uchar4 *rcand = im.cand + (size_t)pf * W;
+    const int c = t * PL_S_T + lane;
+    // the chain's words of pixels c, c-1, .. c-4 (tile t or t-1: released one tile late, so still there)
+    int n0[4], n1[4];
+    unsigned q4 = 0, ql4 = 0;
+    if (!first && c < W + 4) {
+        const short4 e1 = Ecur1[c];
+        n0[0] = e1.x; n0[1] = e1.y; n0[2] = e1.z; n0[3] = e1.w;
+    } else {
+        n0[0] = n0[1] = n0[2] = n0[3] = 0;
+    }
+    n1[0] = n1[1] = n1[2] = n1[3] = 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const int p = c - k;
+        if (p >= 0 && p < W) {
+            const unsigned up = use + (unsigned)(p / PL_S_T);
+            const uint4 wv = sm.outw[up % PL_S_STAGES][pf][p % PL_S_T];
+            const unsigned wd[4] = {wv.x, wv.y, wv.z, wv.w};
+            if (k <= 1) {
+                const unsigned b4 = (wv.x & 255u) | ((wv.y & 255u) << 8) | ((wv.z & 255u) << 16) | ((wv.w & 255u) << 24);
+                if (k == 0) q4 = b4;
+                else ql4 = b4;
+            }
+#pragma unroll
+            for (int cc = 0; cc < 4; cc++) {
+                const int diff = (int)wd[cc] >> 16;
+                PlTaps tp;
+                if ((unsigned)(diff + PL_DL32_HALF) < 2u * PL_DL32_HALF) tp = pl_unpack_taps6(sm.dl32[diff + PL_DL32_HALF]);
+                else tp = pl_sierra_taps(diff, bleed_magic);
+                // next error row 0 (reference row 1): twos, fours, five, fours, twos at cells x .. x+4;
+                // next error row 1 (reference row 2): twos, threes, twos at cells x+1 .. x+3
+                if (k == 0) n0[cc] += tp.twos;
+                if (k == 1) { n0[cc] += tp.fours; n1[cc] += tp.twos; }
+                if (k == 2) { n0[cc] += tp.five; n1[cc] += tp.threes; }
+                if (k == 3) { n0[cc] += tp.fours; n1[cc] += tp.twos; }
+                if (k == 4) n0[cc] += tp.twos;
+            }
+        }
+    }
+    if (c < W + 4) {
+        En0[c] = make_short4((short)n0[0], (short)n0[1], (short)n0[2], (short)n0[3]);
+        En1[c] = make_short4((short)n1[0], (short)n1[1], (short)n1[2], (short)n1[3]);
+    }
+    if (c < W) {
+        const int x = c;
+        rcand[x] = pl_uc4(q4);
+        const unsigned o4 = pl_u32(rin[x]);
+        unsigned oa4 = 0, na4 = 0, ol4 = 0, oad4 = 0, nad4 = 0;
+        if (!first) {
+            oa4 = pl_u32(rin_up[x]);
+            na4 = pl_u32(rout_up[x]);
+        }
+        if (x > 0) {
+            ol4 = pl_u32(rin[x - 1]);
+            if (!first) {
+                oad4 = pl_u32(rin_up[x - 1]);
+                nad4 = pl_u32(rout_up[x - 1]);
+            }
+        } else {
+            ql4 = 0;
+        }
+        // derivative error of the three neighbours (reference :265-287), see pl_row_pass
+        {
+            const unsigned o = __byte_perm(o4, 0u, canon), qq = __byte_perm(q4, 0u, canon);
+            const unsigned n1o = __byte_perm(oa4, 0u, canon), n1n = __byte_perm(na4, 0u, canon);
+            const unsigned n2o = __byte_perm(oad4, 0u, canon), n2n = __byte_perm(nad4, 0u, canon);
+            const unsigned n3o = __byte_perm(ol4, 0u, canon), n3n = __byte_perm(ql4, 0u, canon);
+            unsigned xs = __dp4a(o, o, __dp4a(qq, qq, 0u)) * 3u;
+            xs = __dp4a(n1o, n1o, __dp4a(n1n, n1n, xs));
+            xs = __dp4a(n2o, n2o, __dp4a(n2n, n2n, xs));
+            xs = __dp4a(n3o, n3o, __dp4a(n3n, n3n, xs));
+            unsigned ys = __dp4a(o, qq, 0u) * 3u;
+            ys = __dp4a(n1o, n1n, __dp4a(n1o, o, __dp4a(n1n, qq, ys)));
+            ys = __dp4a(n2o, n2n, __dp4a(n2o, o, __dp4a(n2n, qq, ys)));
+            ys = __dp4a(n3o, n3n, __dp4a(n3o, o, __dp4a(n3n, qq, ys)));
+            unsigned zs = __dp4a(n1o, qq, __dp4a(n1n, o, 0u));
+            zs = __dp4a(n2o, qq, __dp4a(n2n, o, zs));
+            zs = __dp4a(n3o, qq, __dp4a(n3n, o, zs));
+            acc.derr += xs + 2u * zs - 2u * ys;
+        }
+        if (adaptive) {
+#pragma unroll
+            for (int cc = 0; cc < 4; cc++) {
+                if ((chmask >> cc) & 1) {
+                    const int qc = pl_byte(q4, cc);
+                    const int lq = pl_byte(ql4, cc), aq = pl_byte(na4, cc), dq = pl_byte(nad4, cc);
+                    acc.as0 += pl_absres(qc, 0);
+                    acc.as1 += pl_absres(qc, lq);
+                    acc.as2 += pl_absres(qc, aq);
+                    acc.as3 += pl_absres(qc, (aq + lq) >> 1);
+                    acc.as4 += pl_absres(qc, pl_paeth(aq, dq, lq));
+                }
+            }
+        }
+    }
+}
+
+// A post warp's row: candidates pf0, pf0 + pf_step, ... (NF of them at most), tile by tile behind the chain.
+template <int NF>
+__device__ __forceinline__ void pl_solo_post(PlSoloSmem &sm, int pf0, int pf_step, int chmask, int W, int y, int parity,
+                                             int prev_w, bool adaptive, unsigned bleed_magic, unsigned use) {
+    const int lane = threadIdx.x & 31;
     const int ntiles = (W + PL_S_T - 1) / PL_S_T;
     const int ncell_tiles = (W + 4 + PL_S_T - 1) / PL_S_T;   // the error rows are four cells longer than the row
-    unsigned long long derr = 0;
-    unsigned as0 = 0, as1 = 0, as2 = 0, as3 = 0, as4 = 0;
+    PlPostAcc acc[NF];
+#pragma unroll
+    for (int k = 0; k < NF; k++) acc[k] = PlPostAcc{0ull, 0u, 0u, 0u, 0u, 0u};
 
     for (int t = 0; t < ncell_tiles; t++) {
         if (t < ntiles) {
             const unsigned u = use + (unsigned)t;
             pl_mbar_wait_relaxed(&sm.out_full[u % PL_S_STAGES], (u / PL_S_STAGES) & 1u);
         }
-        const int c = t * PL_S_T + lane;
-        // the chain's words of pixels c, c-1, .. c-4 (tile t or t-1: released one tile late, so still there)
-        int n0[4], n1[4];
-        unsigned q4 = 0, ql4 = 0;
-        if (!first && c < W + 4) {
-            const short4 e1 = Ecur1[c];
-            n0[0] = e1.x; n0[1] = e1.y; n0[2] = e1.z; n0[3] = e1.w;
-        } else {
-            n0[0] = n0[1] = n0[2] = n0[3] = 0;
-        }
-        n1[0] = n1[1] = n1[2] = n1[3] = 0;
+        // (the chain's words of pixels c .. c-4 lie in tile t or t-1: tiles are released one tile late, so still there)
 #pragma unroll
-        for (int k = 0; k < 5; k++) {
-            const int p = c - k;
-            if (p >= 0 && p < W) {
-                const unsigned up = use + (unsigned)(p / PL_S_T);
-                const uint4 wv = sm.outw[up % PL_S_STAGES][pf][p % PL_S_T];
-                const unsigned wd[4] = {wv.x, wv.y, wv.z, wv.w};
-                if (k <= 1) {
-                    const unsigned b4 = (wv.x & 255u) | ((wv.y & 255u) << 8) | ((wv.z & 255u) << 16) | ((wv.w & 255u) << 24);
-                    if (k == 0) q4 = b4;
-                    else ql4 = b4;
-                }
-#pragma unroll
-                for (int cc = 0; cc < 4; cc++) {
-                    const int diff = (int)wd[cc] >> 16;
-                    PlTaps tp;
-                    if ((unsigned)(diff + PL_DL32_HALF) < 2u * PL_DL32_HALF) tp = pl_unpack_taps6(sm.dl32[diff + PL_DL32_HALF]);
-                    else tp = pl_sierra_taps(diff, bleed_magic);
-                    // next error row 0 (reference row 1): twos, fours, five, fours, twos at cells x .. x+4;
-                    // next error row 1 (reference row 2): twos, threes, twos at cells x+1 .. x+3
-                    if (k == 0) n0[cc] += tp.twos;
-                    if (k == 1) { n0[cc] += tp.fours; n1[cc] += tp.twos; }
-                    if (k == 2) { n0[cc] += tp.five; n1[cc] += tp.threes; }
-                    if (k == 3) { n0[cc] += tp.fours; n1[cc] += tp.twos; }
-                    if (k == 4) n0[cc] += tp.twos;
-                }
-            }
-        }
-        if (c < W + 4) {
-            En0[c] = make_short4((short)n0[0], (short)n0[1], (short)n0[2], (short)n0[3]);
-            En1[c] = make_short4((short)n1[0], (short)n1[1], (short)n1[2], (short)n1[3]);
-        }
-        if (c < W) {
-            const int x = c;
-            rcand[x] = pl_uc4(q4);
-            const unsigned o4 = pl_u32(rin[x]);
-            unsigned oa4 = 0, na4 = 0, ol4 = 0, oad4 = 0, nad4 = 0;
-            if (!first) {
-                oa4 = pl_u32(rin_up[x]);
-                na4 = pl_u32(rout_up[x]);
-            }
-            if (x > 0) {
-                ol4 = pl_u32(rin[x - 1]);
-                if (!first) {
-                    oad4 = pl_u32(rin_up[x - 1]);
-                    nad4 = pl_u32(rout_up[x - 1]);
-                }
-            } else {
-                ql4 = 0;
-            }
-            // derivative error of the three neighbours (reference :265-287), see pl_row_pass
-            {
-                const unsigned o = __byte_perm(o4, 0u, canon), qq = __byte_perm(q4, 0u, canon);
-                const unsigned n1o = __byte_perm(oa4, 0u, canon), n1n = __byte_perm(na4, 0u, canon);
-                const unsigned n2o = __byte_perm(oad4, 0u, canon), n2n = __byte_perm(nad4, 0u, canon);
-                const unsigned n3o = __byte_perm(ol4, 0u, canon), n3n = __byte_perm(ql4, 0u, canon);
-                unsigned xs = __dp4a(o, o, __dp4a(qq, qq, 0u)) * 3u;
-                xs = __dp4a(n1o, n1o, __dp4a(n1n, n1n, xs));
-                xs = __dp4a(n2o, n2o, __dp4a(n2n, n2n, xs));
-                xs = __dp4a(n3o, n3o, __dp4a(n3n, n3n, xs));
-                unsigned ys = __dp4a(o, qq, 0u) * 3u;
-                ys = __dp4a(n1o, n1n, __dp4a(n1o, o, __dp4a(n1n, qq, ys)));
-                ys = __dp4a(n2o, n2n, __dp4a(n2o, o, __dp4a(n2n, qq, ys)));
-                ys = __dp4a(n3o, n3n, __dp4a(n3o, o, __dp4a(n3n, qq, ys)));
-                unsigned zs = __dp4a(n1o, qq, __dp4a(n1n, o, 0u));
-                zs = __dp4a(n2o, qq, __dp4a(n2n, o, zs));
-                zs = __dp4a(n3o, qq, __dp4a(n3n, o, zs));
-                derr += xs + 2u * zs - 2u * ys;
-            }
-            if (adaptive) {
-#pragma unroll
-                for (int cc = 0; cc < 4; cc++) {
-                    if ((chmask >> cc) & 1) {
-                        const int qc = pl_byte(q4, cc);
-                        const int lq = pl_byte(ql4, cc), aq = pl_byte(na4, cc), dq = pl_byte(nad4, cc);
-                        as0 += pl_absres(qc, 0);
-                        as1 += pl_absres(qc, lq);
-                        as2 += pl_absres(qc, aq);
-                        as3 += pl_absres(qc, (aq + lq) >> 1);
-                        as4 += pl_absres(qc, pl_paeth(aq, dq, lq));
-                    }
-                }
-            }
+        for (int k = 0; k < NF; k++) {
+            const int pf = pf0 + k * pf_step;
+            if (pf < PL_FILTERS)
+                pl_solo_post_tile(sm, pf, t, chmask, W, y, parity, prev_w, adaptive, bleed_magic, use, acc[k]);
         }
         // give the previous tile back to the chain
         __syncwarp();
@@ -689,28 +716,34 @@ __device__ __forceinline__ void pl_solo_post(PlSoloSmem &sm, int pf, int chmask,
     if (PL_S_ARRIVES(lane) && ncell_tiles == ntiles) pl_mbar_arrive(&sm.out_empty[(use + (unsigned)(ntiles - 1)) % PL_S_STAGES]);
 
 #pragma unroll
-    for (int mk = 1; mk < 32; mk <<= 1) {
-        derr += __shfl_xor_sync(PL_FULL, derr, mk);
-        as0 += __shfl_xor_sync(PL_FULL, as0, mk);
-        as1 += __shfl_xor_sync(PL_FULL, as1, mk);
-        as2 += __shfl_xor_sync(PL_FULL, as2, mk);
-        as3 += __shfl_xor_sync(PL_FULL, as3, mk);
-        as4 += __shfl_xor_sync(PL_FULL, as4, mk);
-    }
-    if (lane == 0) {
-        sm.derr[pf] = derr;
-        sm.asum[pf][0] = as0;
-        sm.asum[pf][1] = as1;
-        sm.asum[pf][2] = as2;
-        sm.asum[pf][3] = as3;
-        sm.asum[pf][4] = as4;
+    for (int k = 0; k < NF; k++) {
+        const int pf = pf0 + k * pf_step;
+        if (pf >= PL_FILTERS) continue;
+        PlPostAcc a = acc[k];
+#pragma unroll
+        for (int mk = 1; mk < 32; mk <<= 1) {
+            a.derr += __shfl_xor_sync(PL_FULL, a.derr, mk);
+            a.as0 += __shfl_xor_sync(PL_FULL, a.as0, mk);
+            a.as1 += __shfl_xor_sync(PL_FULL, a.as1, mk);
+            a.as2 += __shfl_xor_sync(PL_FULL, a.as2, mk);
+            a.as3 += __shfl_xor_sync(PL_FULL, a.as3, mk);
+            a.as4 += __shfl_xor_sync(PL_FULL, a.as4, mk);
+        }
+        if (lane == 0) {
+            sm.derr[pf] = a.derr;
+            sm.asum[pf][0] = a.as0;
+            sm.asum[pf][1] = a.as1;
+            sm.asum[pf][2] = a.as2;
+            sm.asum[pf][3] = a.as3;
+            sm.asum[pf][4] = a.as4;
+        }
     }
 }
 
-template <int FPW>
-__global__ void __launch_bounds__(PlSoloCfg<FPW>::THREADS, PL_S_MIN_BLOCKS(FPW))
+template <int FPW, bool COMPACT>
+__global__ void __launch_bounds__(PlSoloCfg<FPW, COMPACT>::THREADS, PlSoloCfg<FPW, COMPACT>::MIN_BLOCKS)
 pl_k2_solo(const PlImageDev *imgs, const int *slots, int strength, int bleed, unsigned sm_count) {
-    typedef PlSoloCfg<FPW> C;
+    typedef PlSoloCfg<FPW, COMPACT> C;
     PL_DYN_SMEM(smem_raw);
     PlSoloSmem &sm = *(PlSoloSmem *)pl_align_shared(smem_raw, 16);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -718,7 +751,7 @@ pl_k2_solo(const PlImageDev *imgs, const int *slots, int strength, int bleed, un
     if (idx < 0) return;
     // (CTAs are placed round-robin over the SMs, so the CTAs that share an SM differ in blockIdx / #SMs)
     const int role = C::role(warp, (int)((blockIdx.x / sm_count) & 3u));
-    const int pf = role >= 0 ? role : -1;   // candidate this warp post-processes (-1: none)
+    const int pw = role >= 0 ? role : -1;   // post warp index (-1: none): takes candidates pw, pw + NPOSTW, ...
 
     // ---- set-up ------------------------------------------------------------------------------------------------
     if (tid == 0) {
@@ -727,7 +760,7 @@ pl_k2_solo(const PlImageDev *imgs, const int *slots, int strength, int bleed, un
             pl_mbar_init(&sm.pre_full[s], PL_S_ARRIVERS);
             pl_mbar_init(&sm.pre_empty[s], C::NCHAIN * PL_S_ARRIVERS);
             pl_mbar_init(&sm.out_full[s], C::NCHAIN * PL_S_ARRIVERS);
-            pl_mbar_init(&sm.out_empty[s], PL_S_POSTW * PL_S_ARRIVERS);
+            pl_mbar_init(&sm.out_empty[s], C::NPOSTW * PL_S_ARRIVERS);
         }
         pl_fence_mbar_init();
     }
@@ -835,22 +868,24 @@ pl_k2_solo(const PlImageDev *imgs, const int *slots, int strength, int bleed, un
                 try_fast = 4u * g <= 3u * (unsigned)W || (y & 15) == 15;
             } else if (role == -1) {
                 pl_solo_producer(sm, W, y, y & 1, prev_w, use);
-            } else if (pf >= 0) {
-                pl_solo_post(sm, pf, chmask, W, y, y & 1, prev_w, adaptive, bleed_magic, use);
+            } else if (pw >= 0) {
+                pl_solo_post<C::NF>(sm, pw, C::NPOSTW, chmask, W, y, y & 1, prev_w, adaptive, bleed_magic, use);
             }
             use += (unsigned)ntiles;
             __syncthreads();
 
             // ---- row cost (reference src/optimize_state.c:314-360), see pl_row_pass: a post warp takes its candidate
-            if (pf >= 0) {
-                unsigned bits = 0;
-                for (int s = lane; s < 256; s += 32) {
-                    const unsigned hv = (unsigned)(sm.hk[pf][s] >> 32);
-                    bits += (hv - sm.base[s]) * (33u + (unsigned)__clz((int)hv));
-                }
+            if (pw >= 0) {
+                for (int pf = pw; pf < PL_FILTERS; pf += C::NPOSTW) {
+                    unsigned bits = 0;
+                    for (int s = lane; s < 256; s += 32) {
+                        const unsigned hv = (unsigned)(sm.hk[pf][s] >> 32);
+                        bits += (hv - sm.base[s]) * (33u + (unsigned)__clz((int)hv));
+                    }
 #pragma unroll
-                for (int mk = 1; mk < 32; mk <<= 1) bits += __shfl_xor_sync(PL_FULL, bits, mk);
-                if (lane == 0) sm.bits[pf] = bits;
+                    for (int mk = 1; mk < 32; mk <<= 1) bits += __shfl_xor_sync(PL_FULL, bits, mk);
+                    if (lane == 0) sm.bits[pf] = bits;
+                }
             }
             __syncthreads();
             // ---- the winner (reference src/pngloss_image.c:257-263): strict < in filter order ---------------------

@@ -26,7 +26,7 @@ extern "C" int emu_optimize(unsigned char *rgba, int n, uint32_t w, uint32_t h,
     // in-place batch (the output buffer is the input buffer), + 64 for the lean kernel (pl_k2_lean, lpc 1)
     // + 128 for the latency kernel (pl_k2_solo<5>: one chain warp), + 256 for pl_k2_solo<1> (five chain warps)
     const bool bm = (lpc & 16) != 0, in_place = (lpc & 32) != 0, lean = (lpc & 64) != 0;
-    const int solo = (lpc & 128) ? 5 : (lpc & 256) ? 1 : 0;
+    const int solo = (lpc & 128) ? 5 : (lpc & 256) ? 1 : (lpc & 512) ? 4 : 0;   // + 512: the four-warp layout
     lpc &= 15;
     if (solo) lpc = 8;   // one image per CTA
     if (lean && (lpc != 1 || (w & 3))) return -2;
@@ -70,11 +70,14 @@ extern "C" int emu_optimize(unsigned char *rgba, int n, uint32_t w, uint32_t h,
     if (solo) {
         const int *dslots = slots.data();
         if (solo == 5)
-            simt::launch([&] { pl_k2_solo<5>(dimgs, dslots, strength, bleed, 2u); }, dim3(nblocks),
-                         dim3(PlSoloCfg<5>::THREADS), sizeof(PlSoloSmem) + 16);
+            simt::launch([&] { pl_k2_solo<5, false>(dimgs, dslots, strength, bleed, 2u); }, dim3(nblocks),
+                         dim3(PlSoloCfg<5, false>::THREADS), sizeof(PlSoloSmem) + 16);
+        else if (solo == 4)
+            simt::launch([&] { pl_k2_solo<5, true>(dimgs, dslots, strength, bleed, 2u); }, dim3(nblocks),
+                         dim3(PlSoloCfg<5, true>::THREADS), sizeof(PlSoloSmem) + 16);
         else
-            simt::launch([&] { pl_k2_solo<1>(dimgs, dslots, strength, bleed, 2u); }, dim3(nblocks),
-                         dim3(PlSoloCfg<1>::THREADS), sizeof(PlSoloSmem) + 16);
+            simt::launch([&] { pl_k2_solo<1, false>(dimgs, dslots, strength, bleed, 2u); }, dim3(nblocks),
+                         dim3(PlSoloCfg<1, false>::THREADS), sizeof(PlSoloSmem) + 16);
     } else if (lean) {
         const int *dslots = slots.data();
         simt::launch([&] { pl_k2_lean(dimgs, dslots, strength, bleed); }, dim3(nblocks), dim3(PL_K2_THREADS),

@@ -666,7 +666,7 @@ def test_lean_kernel_4k_golden_24_images(ctx, oracle):
 
 
 # ---- the latency kernel (pl_k2_solo.cuh) -------------------------------------------------------------------------
-@pytest.mark.parametrize("solo", [1, 2], ids=["one-chain-warp", "five-chain-warps"])
+@pytest.mark.parametrize("solo", [1, 2, 3], ids=["one-chain-warp", "five-chain-warps", "four-warp-cta"])
 def test_solo_kernel_golden_and_random(ctx, oracle, solo):
     """The latency kernel (pl_k2_solo: one image per CTA, chain / producer / post warps, fast path + general path)
     against the reference's goldens - every small and medium vector of strength 0 .. 126, through the
@@ -733,7 +733,7 @@ def test_solo_kernel_golden_and_random(ctx, oracle, solo):
     ctx.set_solo(-1)
 
 
-@pytest.mark.parametrize("solo", [1, 2], ids=["one-chain-warp", "five-chain-warps"])
+@pytest.mark.parametrize("solo", [1, 3], ids=["one-chain-warp", "four-warp-cta"])
 def test_solo_kernel_suite_images(ctx, oracle, solo):
     """The eight full suite images (tier "suite" goldens of the unmodified reference) through the latency kernel."""
     ctx.set_lanes(8)

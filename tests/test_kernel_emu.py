@@ -308,6 +308,7 @@ def test_emu_lean_full_rgba_ctas(emu, oracle):
 # ---- the latency kernel (pl_k2_solo.cuh): one image per CTA, chain / producer / post warps ----------------------
 SOLO5 = 128   # emu flag: pl_k2_solo<5> (one chain warp carries the five candidates)
 SOLO1 = 256   # emu flag: pl_k2_solo<1> (one chain warp per candidate)
+SOLOC = 512   # emu flag: pl_k2_solo<5, compact> (four warps: chain, producer, two post warps)
 
 SOLO_CASES = CASES + [
     (32, 3, 31, 4, 20, 2, False),    # exactly one tile: the error rows' four extra cells need a tile of their own
@@ -320,7 +321,7 @@ SOLO_CASES = CASES + [
 ]
 
 
-@pytest.mark.parametrize("flag", [SOLO5, SOLO1], ids=["one-chain-warp", "five-chain-warps"])
+@pytest.mark.parametrize("flag", [SOLO5, SOLO1, SOLOC], ids=["one-chain-warp", "five-chain-warps", "four-warp-cta"])
 @pytest.mark.parametrize("case", SOLO_CASES, ids=lambda c: "w%d-h%d-seed%d-bpp%d-s%d-b%d-null%d" % c)
 def test_emu_solo_single_image(emu, oracle, case, flag):
     w, h, seed, bpp, s, b, nf = case
@@ -329,13 +330,13 @@ def test_emu_solo_single_image(emu, oracle, case, flag):
     assert got["status"][0][1] == bpp or (w * h == 1)
 
 
-@pytest.mark.parametrize("flag", [SOLO5, SOLO1, IN_PLACE + SOLO5, IN_PLACE + SOLO1])
+@pytest.mark.parametrize("flag", [SOLO5, SOLO1, SOLOC, IN_PLACE + SOLO5, IN_PLACE + SOLO1, IN_PLACE + SOLOC])
 def test_emu_solo_batch_mixed_modes(emu, oracle, flag):
     imgs = [to_bpp(oracle.synth(70, 6, 100 + i), (i % 4) + 1) for i in range(6)]
     compare(emu, oracle, imgs, 20, 2, False, flag)
 
 
-@pytest.mark.parametrize("flag", [SOLO5, SOLO1])
+@pytest.mark.parametrize("flag", [SOLO5, SOLO1, SOLOC])
 def test_emu_solo_retry_path(emu, oracle, flag):
     rng = np.random.default_rng(7)
     imgs, retried = [], 0
@@ -352,7 +353,7 @@ def test_emu_solo_retry_path(emu, oracle, flag):
     assert (got["status"][:, 2] > 0).sum() == retried
 
 
-@pytest.mark.parametrize("flag", [SOLO5, SOLO1])
+@pytest.mark.parametrize("flag", [SOLO5, SOLO1, SOLOC])
 def test_emu_solo_noise_ties_and_paths(emu, oracle, flag):
     """Frequency ties, noise (the seam), fully transparent pixels, clamped bands; the look-up, the scan, both bucket
     updates, the fix-up replay and both tap paths must all have run."""

@@ -18,7 +18,7 @@ def main():
     ap.add_argument("--lanes", default="8,4,2,1")
     ap.add_argument("--bm", default="-1", help="bucket-maxima modes to sweep: -1 library default, 0 off, 1 on")
     ap.add_argument("--lean", default="-1", help="lean-kernel modes to sweep: -1 library default, 0 generic kernel, 1 lean")
-    ap.add_argument("--solo", default="0", help="latency-kernel modes to sweep: 0 off, 1 one chain warp, 2 five chain warps")
+    ap.add_argument("--solo", default="0", help="latency-kernel modes to sweep: 0 off, 1 one chain warp, 2 five chain warps, 3 four-warp CTA")
     ap.add_argument("--strength", type=int, default=20)
     ap.add_argument("--reps", type=int, default=1)
     ap.add_argument("--profile", action="store_true", help="with a -DPL_K2_PROFILE build: per-filter busy cycles")
