@@ -288,7 +288,7 @@ __device__ __forceinline__ void pl_mbar_wait_relaxed(unsigned long long *bar, un
             : "r"(a), "r"(parity)
             : "memory");
         if (done) break;
-        __nanosleep(2000);
+        __nanosleep(400);
     }
 #endif
 }
