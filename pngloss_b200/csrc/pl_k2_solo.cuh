@@ -1,11 +1,11 @@
-// K2, latency variant ("K2S"): the quantise + filter-search kernel for batches that leave every image an SM of
-// its own - the reference's actual use (one image per call, src/pngloss.c:173-205,266) and the few-large-image
-// configurations.
+// K2, latency variant ("K2S"): the quantise + filter-search kernel for batches that leave every image a CTA of
+// its own (up to four per SM) - the reference's actual use (one image per call, src/pngloss.c:173-205,266), the
+// few-large-image configurations, command lines over a few hundred files.
 //
 // Same algorithm and bit-identical results as pl_k2_quantize / pl_k2_lean.  Those kernels let one warp do
 // everything a candidate row needs.  A lone warp issues one instruction about every four cycles (fixed-latency
 // dependencies, in-order issue: every exposed shared-memory or branch latency is paid in full), so a pixel step
-// costs (instructions on that warp) x 4 cycles ~ 1000 cycles whatever the lane mapping.  Here the roles are split
+// costs (instructions on that warp) x 3-4 cycles ~ 1000 cycles whatever the lane mapping.  Here the roles are split
 // across the warps of one CTA (one image per CTA) and the one warp that carries the serial chain executes as few
 // instructions as the algorithm allows:
 //   * chain warp(s): a lane is (filter, channel); the bucket-maxima look-up (pl_kernels.cuh) needs no candidate
@@ -17,9 +17,11 @@
 //     per-pass look-up tables in shared memory; every table is addressed by 32-bit shared address.
 //   * a producer warp, tiles ahead: packs original row y, quantised row y-1 and the previous winner's error row 0
 //     into those words (ring of PL_S_STAGES tiles, mbarrier hand-off).
-//   * five post warps (one per candidate), tiles behind, one lane per pixel: everything that is separable - the
+//   * post warps (five, one per candidate; two in the four-warp layout), tiles behind, one lane per pixel: everything
+//     that is separable - the
 //     two outgoing error rows are a 5-tap / 3-tap stencil over the differences (src/optimize_state.c:445-467),
 //     the derivative error (:265-287), libpng's heuristic sums (:492-562), the candidate row.
+// Strengths 0 .. 126 (the bucket tables have room for the one-symbol buckets of strength 0).
 // The row end (cost, winner, commit, histogram clone, table rebuild) is done by all warps between CTA barriers.
 //
 // Replaces the same reference code as K2: src/pngloss_image.c:159-309, src/optimize_state.c:114-361,390-562.
