@@ -205,6 +205,7 @@ __device__ __forceinline__ void pl_fence_mbar_init() {
 typedef unsigned char *PlSh;
 __device__ __forceinline__ PlSh pl_sh(void *p) { return (unsigned char *)p; }
 __device__ __forceinline__ PlSh pl_sh_opaque(PlSh a) { return a; }
+__device__ __forceinline__ PlSh pl_sh_select(PlSh a, PlSh b, unsigned mask) { return mask ? a : b; }
 __device__ __forceinline__ uint32_t pl_lds32(PlSh a) { return *(volatile uint32_t *)a; }
 __device__ __forceinline__ unsigned long long pl_lds64(PlSh a) { return *(volatile unsigned long long *)a; }
 __device__ __forceinline__ uint4 pl_lds128(PlSh a) {
@@ -255,6 +256,8 @@ __device__ __forceinline__ void pl_atoms_inc32(PlSh a) {
 __device__ __forceinline__ void pl_atoms_max32(PlSh a, uint32_t v) {
     asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
+// a where mask is all ones, b where it is zero: one LOP3, no predicate
+__device__ __forceinline__ PlSh pl_sh_select(PlSh a, PlSh b, unsigned mask) { return (a & mask) | (b & ~mask); }
 // unconditional forms for the chain warp (a predicate would become a branch around the instruction): add 0 / max
 // with 0 are no-ops
 __device__ __forceinline__ void pl_atoms_add32(PlSh a, uint32_t v) {

@@ -47,7 +47,8 @@
 #define PL_S_TAPC_HALF 512 // the chain's tap table covers differences -512 .. 511
 #define PL_S_BOFF 1024     // the band table covers here - predicted = -1024 .. 1023
 #define PL_S_HPAD 4        // entries between the candidates' histograms (bank stagger)
-#define PL_S_BM_ROW 264     // entries of a candidate's bucket table: up to 129 + 130 buckets (strength 0) + Z+
+#define PL_S_BM_ROW 260     // entries of a candidate's bucket table: up to 129 + 130 buckets (strength 0) + Z+; like the
+                            // histograms' row, 8 banks (mod 32) per candidate: the candidates of a half-warp never collide
 
 // Warp roles.  The hardware arbiter prefers the higher warp id of a sub-partition (warp id % 4), so a chain warp is the
 // higher warp of its sub-partition.
@@ -108,13 +109,15 @@ struct PlSoloSmem {
     uint32_t tapc[2 * PL_S_TAPC_HALF];      // chain: difference -> the two taps that stay in the row (rem | threes << 16)
     uint32_t dl32[2 * PL_DL32_HALF];        // post warps: all five taps (pl_pack_taps6)
     uint4 pre[PL_S_STAGES][PL_S_T + 1];     // per pixel, word ch: orig | above << 8 | incoming error << 16
-    uint4 outw[PL_S_STAGES][PL_FILTERS][PL_S_T];   // per candidate and pixel, word ch: back | difference << 16
+    uint4 outw[PL_S_STAGES][PL_FILTERS][PL_S_T + 1];   // per candidate and pixel, word ch: back | difference << 16
+                                                       // (+ 1: the candidates' rows are 4 banks apart)
     unsigned long long pre_full[PL_S_STAGES], pre_empty[PL_S_STAGES];
     unsigned long long out_full[PL_S_STAGES], out_empty[PL_S_STAGES];
     unsigned long long derr[PL_FILTERS];
     unsigned asum[PL_FILTERS][5];
     unsigned bits[PL_FILTERS];
     uint4 trash[PL_S_T];                    // where the idle lanes of a chain warp store
+    uint32_t sink[32];                      // ... and where a lane without an active channel sends its atomics (a word each)
     PlImageDev img;
 };
 
@@ -170,7 +173,7 @@ __device__ __forceinline__ unsigned pl_solo_band_entry(const PlBm &bmc, int want
 }
 
 // Commit of a byte: count the symbol, and let its new key (count `now`, rank) enter every table entry that holds its
-// bin.  No predicates (they would become branches): an inactive lane (actm = 0) adds 0, a key that must not enter is 0.
+// bin.  No predicates (they would become branches): a key that must not enter is 0.
 // `three`: some bin of this strength has a third entry (warp-uniform).  The loads are a call of their own: the fast
 // path issues them for its provisional symbol before the channel vote, so that their latency is not exposed.
 struct PlBinLoaded { uint4 bi; unsigned long long bj; };
@@ -182,18 +185,20 @@ __device__ __forceinline__ PlBinLoaded pl_solo_bin_load(PlSh bins_sh, PlSh bins3
     return r;
 }
 __device__ __forceinline__ void pl_solo_commit(PlSh hk_sh, PlSh bm_sh, const PlBinLoaded &ld, int sym, unsigned now,
-                                               unsigned rank7, unsigned actm, bool three) {
+                                               unsigned rank7, unsigned actm, PlSh sink_sh, bool three) {
+    // A lane without an active channel (actm = 0) sends its atomics to a word of its own: on the real tables they would
+    // be no-ops, but atomics on one address are served one after the other.
     const unsigned bin = (unsigned)sym & 255u;
     const uint4 bi = ld.bi;
-    pl_atoms_add32(hk_sh + bin * 8u + 4u, actm & 1u);
-    const unsigned k0 = (((now - bi.y) << PL_BM_COUNT_SHIFT) | rank7 | (bi.x & 127u)) & actm;
-    const unsigned k1 = (((now - bi.w) << PL_BM_COUNT_SHIFT) | rank7 | (bi.z & 127u)) & actm;
-    pl_atoms_max32(bm_sh + (bi.x >> 16), now >= bi.y ? k0 : 0u);
-    pl_atoms_max32(bm_sh + (bi.z >> 16), now >= bi.w ? k1 : 0u);
+    pl_atoms_add32(pl_sh_select(hk_sh + bin * 8u + 4u, sink_sh, actm), 1u);
+    const unsigned k0 = ((now - bi.y) << PL_BM_COUNT_SHIFT) | rank7 | (bi.x & 127u);
+    const unsigned k1 = ((now - bi.w) << PL_BM_COUNT_SHIFT) | rank7 | (bi.z & 127u);
+    pl_atoms_max32(pl_sh_select(bm_sh + (bi.x >> 16), sink_sh, actm), now >= bi.y ? k0 : 0u);
+    pl_atoms_max32(pl_sh_select(bm_sh + (bi.z >> 16), sink_sh, actm), now >= bi.w ? k1 : 0u);
     if (three) {
         const unsigned e2 = (unsigned)ld.bj, b2 = (unsigned)(ld.bj >> 32);
-        const unsigned k2 = (((now - b2) << PL_BM_COUNT_SHIFT) | rank7 | (e2 & 127u)) & actm;
-        pl_atoms_max32(bm_sh + (e2 >> 16), now >= b2 ? k2 : 0u);
+        const unsigned k2 = ((now - b2) << PL_BM_COUNT_SHIFT) | rank7 | (e2 & 127u);
+        pl_atoms_max32(pl_sh_select(bm_sh + (e2 >> 16), sink_sh, actm), now >= b2 ? k2 : 0u);
     }
 }
 
@@ -231,6 +236,7 @@ __device__ __forceinline__ unsigned pl_solo_chain(PlSoloSmem &sm, int f, int ch,
     const PlSh band_sh = pl_sh_opaque(pl_sh(sm.band));
     const PlSh tapc_sh = pl_sh_opaque(pl_sh(sm.tapc + PL_S_TAPC_HALF));
     const unsigned actm = act ? ~0u : 0u;   // as a mask: predicates are scarce and get recomputed
+    const PlSh sink_sh = pl_sh_opaque(pl_sh(&sm.sink[lane]));
     // predictor of this lane's candidate, branch-free (FPW = 5: the lanes of a warp differ)
     const int ma = (ff == 2 || ff == 3) ? 255 : 0, ml = (ff == 1 || ff == 3) ? 255 : 0, sh = ff == 3 ? 1 : 0;
     const unsigned pm = ff == 4 ? ~0u : 0u;
@@ -388,7 +394,7 @@ __device__ __forceinline__ unsigned pl_solo_chain(PlSoloSmem &sm, int f, int ch,
                         diff = (transp || !act) ? 0 : want - sym;   // (a replayed symbol lies in the band: within the table)
                         te = pl_lds32(tapc_sh + diff * 4);
                     }
-                    pl_solo_commit(hk_sh, bm_sh, ld, sym, bc + 1u, rk << 7, actm, three);
+                    pl_solo_commit(hk_sh, bm_sh, ld, sym, bc + 1u, rk << 7, actm, sink_sh, three);
                     back &= (int)actm;
                     pl_sts32(po + (unsigned)i * 16u, ((unsigned)back & 255u) | ((unsigned)diff << 16));
                     left = back;
@@ -502,7 +508,7 @@ __device__ __forceinline__ unsigned pl_solo_chain(PlSoloSmem &sm, int f, int ch,
                 diff = (act && !transp) ? pl_sext16(want - sym) : 0;   // here - back (0 for a transparent pixel)
                 back = act ? sym + pred : 0;
                 pl_solo_commit(hk_sh, bm_sh, pl_solo_bin_load(bins_sh, bins3_sh, sym, three), sym, bc + 1u,
-                               (bl >> (PL_KEY_RANK_SHIFT - 7)) & (255u << 7), actm, three);
+                               (bl >> (PL_KEY_RANK_SHIFT - 7)) & (255u << 7), actm, sink_sh, three);
             }
 
             pl_sts32(po + (unsigned)i * 16u, ((unsigned)back & 255u) | ((unsigned)diff << 16));
