@@ -191,14 +191,16 @@ __device__ __forceinline__ void pl_solo_commit(PlSh hk_sh, PlSh bm_sh, const PlB
     const unsigned bin = (unsigned)sym & 255u;
     const uint4 bi = ld.bi;
     pl_atoms_add32(pl_sh_select(hk_sh + bin * 8u + 4u, sink_sh, actm), 1u);
+    // (an entry that does not exist - base 0xffffffff - or that the key must not enter goes to the sink too: all such
+    // lanes would otherwise meet on entry 0 of their candidate's row)
     const unsigned k0 = ((now - bi.y) << PL_BM_COUNT_SHIFT) | rank7 | (bi.x & 127u);
     const unsigned k1 = ((now - bi.w) << PL_BM_COUNT_SHIFT) | rank7 | (bi.z & 127u);
-    pl_atoms_max32(pl_sh_select(bm_sh + (bi.x >> 16), sink_sh, actm), now >= bi.y ? k0 : 0u);
-    pl_atoms_max32(pl_sh_select(bm_sh + (bi.z >> 16), sink_sh, actm), now >= bi.w ? k1 : 0u);
+    pl_atoms_max32(pl_sh_select(bm_sh + (bi.x >> 16), sink_sh, now >= bi.y ? actm : 0u), k0);
+    pl_atoms_max32(pl_sh_select(bm_sh + (bi.z >> 16), sink_sh, now >= bi.w ? actm : 0u), k1);
     if (three) {
         const unsigned e2 = (unsigned)ld.bj, b2 = (unsigned)(ld.bj >> 32);
         const unsigned k2 = ((now - b2) << PL_BM_COUNT_SHIFT) | rank7 | (e2 & 127u);
-        pl_atoms_max32(pl_sh_select(bm_sh + (e2 >> 16), sink_sh, actm), now >= b2 ? k2 : 0u);
+        pl_atoms_max32(pl_sh_select(bm_sh + (e2 >> 16), sink_sh, now >= b2 ? actm : 0u), k2);
     }
 }
 
