@@ -752,6 +752,46 @@ def test_solo_kernel_suite_images(ctx, oracle, solo):
     ctx.set_solo(-1)
 
 
+def test_kernel_choice_by_batch_size(ctx, oracle):
+    """The library's own choice of the quantise kernel (pl_api.cu use_solo / choose_lpc): the latency kernel while
+    every image can have a CTA of its own with at most four CTAs per SM and the strength is at most 126, the generic
+    kernel (several images per CTA) beyond, and whenever a lane mapping is set explicitly."""
+    sms = 148
+    img = oracle.synth(16, 4, 3)
+    want_px, want_rf = oracle.optimize(img, 20, 2, True)
+
+    def run(n, strength=20):
+        batch = pngloss_b200.Batch(ctx, [16] * n, [4] * n)
+        for i in range(n):
+            batch.upload(i, img)
+        batch.run(strength, 2)
+        st, _, _ = batch.finish()
+        assert (st == 0).all()
+        info = batch.launch_info()
+        if strength == 20:
+            out = np.zeros_like(img)
+            rf = np.zeros(4, np.uint8)
+            batch.download(n - 1, out, rf)
+            ctx.sync()
+            assert np.array_equal(out, want_px) and np.array_equal(rf, want_rf)
+        batch.close()
+        return info
+
+    ctx.set_lanes(0)
+    ctx.set_solo(-1)
+    assert run(1)["solo"] and run(2 * sms)["solo"] and run(4 * sms)["solo"]
+    assert run(1, 0)["solo"] and run(1, 126)["solo"]
+    big = run(4 * sms + 1)
+    assert not big["solo"] and big["images_per_cta"] > 1
+    assert not run(1, 127)["solo"]
+    ctx.set_lanes(8)
+    assert not run(1)["solo"]            # an explicit lane mapping keeps the generic kernel
+    ctx.set_solo(0)
+    ctx.set_lanes(0)
+    assert not run(1)["solo"]
+    ctx.set_solo(-1)
+
+
 def test_full_8192x8192_golden(ctx, oracle):
     """BASELINE configs[4]'s image size in full: one 8192 x 8192 synthetic image (seed 1000, strength 20) through
     the device-resident batch must hash to what the unmodified reference produced (tier "huge" golden, made by
